@@ -1,0 +1,263 @@
+// api.cu — context lifecycle, error reporting, profiling records, NCCL plumbing.
+#include "common.cuh"
+
+namespace salg {
+
+static thread_local std::string g_last_error;
+
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+
+static const char* kProfNames[PROF_NCLS] = {
+    "spmm", "spmm_t", "gram", "chol", "panel_mul", "jacobi", "stats", "transpose",
+    "compact", "elementwise", "allreduce", "h2d", "spmv", "other"};
+
+ProfScope::ProfScope(salg_ctx* c, int cls, double bytes) : ctx(c) {
+    if (!ctx->prof_on) return;
+    ProfRecord r;
+    r.cls = cls;
+    r.bytes = bytes;
+    auto get_event = [&]() {
+        cudaEvent_t e;
+        if (!ctx->event_pool.empty()) {
+            e = ctx->event_pool.back();
+            ctx->event_pool.pop_back();
+        } else {
+            if (cudaEventCreate(&e) != cudaSuccess) e = nullptr;
+        }
+        return e;
+    };
+    r.e0 = get_event();
+    r.e1 = get_event();
+    if (!r.e0 || !r.e1) return;
+    cudaEventRecord(r.e0, ctx->stream);
+    ctx->prof_pending.push_back(r);
+    idx = (int)ctx->prof_pending.size() - 1;
+}
+
+ProfScope::~ProfScope() {
+    if (idx >= 0) cudaEventRecord(ctx->prof_pending[idx].e1, ctx->stream);
+}
+
+void prof_collect(salg_ctx* ctx) {
+    for (auto& r : ctx->prof_pending) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(r.e1) == cudaSuccess &&
+            cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+            ctx->prof_ms[r.cls] += ms;
+            ctx->prof_launches[r.cls] += 1;
+            ctx->prof_bytes[r.cls] += r.bytes;
+        }
+        ctx->event_pool.push_back(r.e0);
+        ctx->event_pool.push_back(r.e1);
+    }
+    ctx->prof_pending.clear();
+}
+
+void allreduce_f64(salg_ctx* ctx, double* buf, size_t n) {
+    if (ctx->nranks <= 1 || n == 0) return;
+    ProfScope ps(ctx, PROF_ALLREDUCE, (double)n * 8);
+    SALG_NCCL(ncclAllReduce(buf, buf, n, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+}
+
+template <>
+void allreduce_T<float>(salg_ctx* ctx, float* buf, size_t n) {
+    if (ctx->nranks <= 1 || n == 0) return;
+    ProfScope ps(ctx, PROF_ALLREDUCE, (double)n * 4);
+    SALG_NCCL(ncclAllReduce(buf, buf, n, ncclFloat, ncclSum, ctx->comm, ctx->stream));
+}
+template <>
+void allreduce_T<double>(salg_ctx* ctx, double* buf, size_t n) {
+    allreduce_f64(ctx, buf, n);
+}
+
+static salg_ctx* ctx_new(int device) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        throw Error(SALG_ERR_CUDA,
+                    std::string("no CUDA device available (libsalg_b200 has no CPU fallback): ") +
+                        cudaGetErrorString(e));
+    SALG_REQUIRE(device >= 0 && device < ndev, SALG_ERR_BAD_ARG, "device index out of range");
+    SALG_CUDA(cudaSetDevice(device));
+    salg_ctx* c = new salg_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    SALG_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    SALG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    SALG_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    // keep freed temporaries cached in the stream-ordered pool
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    return c;
+}
+
+}  // namespace salg
+
+using namespace salg;
+
+extern "C" {
+
+const char* salg_last_error(void) { return g_last_error.c_str(); }
+
+int salg_version(void) { return SALG_VERSION; }
+
+int salg_device_count(int* out) {
+    return guarded([&] {
+        SALG_REQUIRE(out, SALG_ERR_BAD_ARG, "out is NULL");
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            n = 0;
+        }
+        *out = n;
+    });
+}
+
+int salg_ctx_create(int device, salg_ctx** out) {
+    return guarded([&] {
+        SALG_REQUIRE(out, SALG_ERR_BAD_ARG, "out is NULL");
+        *out = ctx_new(device);
+    });
+}
+
+int salg_nccl_unique_id(void* out128) {
+    return guarded([&] {
+        SALG_REQUIRE(out128, SALG_ERR_BAD_ARG, "out is NULL");
+        static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+        ncclUniqueId id;
+        SALG_NCCL(ncclGetUniqueId(&id));
+        memcpy(out128, &id, sizeof(id));
+    });
+}
+
+int salg_ctx_create_dist(int device, int rank, int nranks, const void* uid, salg_ctx** out) {
+    return guarded([&] {
+        SALG_REQUIRE(out, SALG_ERR_BAD_ARG, "out is NULL");
+        SALG_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, SALG_ERR_BAD_ARG, "bad rank/nranks");
+        salg_ctx* c = ctx_new(device);
+        c->rank = rank;
+        c->nranks = nranks;
+        if (nranks > 1) {
+            SALG_REQUIRE(uid, SALG_ERR_BAD_ARG, "nccl_unique_id is NULL");
+            ncclUniqueId id;
+            memcpy(&id, uid, sizeof(id));
+            ncclResult_t r = ncclCommInitRank(&c->comm, nranks, id, rank);
+            if (r != ncclSuccess) {
+                std::string m = std::string("ncclCommInitRank failed: ") + ncclGetErrorString(r);
+                salg_ctx_destroy(c);
+                throw Error(SALG_ERR_NCCL, m);
+            }
+        }
+        *out = c;
+    });
+}
+
+int salg_ctx_destroy(salg_ctx* c) {
+    return guarded([&] {
+        if (!c) return;
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(c->stream);
+        prof_collect(c);
+        for (auto e : c->event_pool) cudaEventDestroy(e);
+        if (c->timer0) cudaEventDestroy(c->timer0);
+        if (c->timer1) cudaEventDestroy(c->timer1);
+        for (int i = 0; i < salg_ctx::N_STAGE; i++) {
+            if (c->stage[i]) cudaFreeHost(c->stage[i]);
+            if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
+        }
+        if (c->comm) ncclCommDestroy(c->comm);
+        if (c->stream) cudaStreamDestroy(c->stream);
+        if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+        delete c;
+    });
+}
+
+int salg_ctx_sync(salg_ctx* c) {
+    return guarded([&] {
+        SALG_REQUIRE(c, SALG_ERR_BAD_ARG, "ctx is NULL");
+        SALG_CUDA(cudaStreamSynchronize(c->stream));
+    });
+}
+
+int salg_ctx_rank(const salg_ctx* c, int* rank, int* nranks) {
+    return guarded([&] {
+        SALG_REQUIRE(c, SALG_ERR_BAD_ARG, "ctx is NULL");
+        if (rank) *rank = c->rank;
+        if (nranks) *nranks = c->nranks;
+    });
+}
+
+int salg_prof_enable(salg_ctx* c, int on) {
+    return guarded([&] {
+        SALG_REQUIRE(c, SALG_ERR_BAD_ARG, "ctx is NULL");
+        c->prof_on = on != 0;
+    });
+}
+
+int salg_prof_reset(salg_ctx* c) {
+    return guarded([&] {
+        SALG_REQUIRE(c, SALG_ERR_BAD_ARG, "ctx is NULL");
+        prof_collect(c);
+        for (int i = 0; i < PROF_NCLS; i++) {
+            c->prof_ms[i] = 0;
+            c->prof_launches[i] = 0;
+            c->prof_bytes[i] = 0;
+        }
+    });
+}
+
+int salg_timer_start(salg_ctx* c) {
+    return guarded([&] {
+        SALG_REQUIRE(c, SALG_ERR_BAD_ARG, "ctx is NULL");
+        SALG_CUDA(cudaSetDevice(c->device));
+        if (!c->timer0) {
+            SALG_CUDA(cudaEventCreate(&c->timer0));
+            SALG_CUDA(cudaEventCreate(&c->timer1));
+        }
+        SALG_CUDA(cudaStreamSynchronize(c->stream));
+        SALG_CUDA(cudaEventRecord(c->timer0, c->stream));
+    });
+}
+
+int salg_timer_stop(salg_ctx* c, double* ms) {
+    return guarded([&] {
+        SALG_REQUIRE(c && ms && c->timer0, SALG_ERR_BAD_ARG, "timer not started");
+        SALG_CUDA(cudaEventRecord(c->timer1, c->stream));
+        SALG_CUDA(cudaEventSynchronize(c->timer1));
+        float f = 0.f;
+        SALG_CUDA(cudaEventElapsedTime(&f, c->timer0, c->timer1));
+        *ms = (double)f;
+    });
+}
+
+int salg_launch_count(salg_ctx* c, int64_t* out) {
+    return guarded([&] {
+        SALG_REQUIRE(c && out, SALG_ERR_BAD_ARG, "NULL argument");
+        *out = c->n_launch;
+    });
+}
+
+int salg_prof_count(void) { return PROF_NCLS; }
+
+const char* salg_prof_name(int cls) {
+    if (cls < 0 || cls >= PROF_NCLS) return "";
+    return kProfNames[cls];
+}
+
+int salg_prof_get(salg_ctx* c, int cls, double* ms, int64_t* launches, double* bytes) {
+    return guarded([&] {
+        SALG_REQUIRE(c, SALG_ERR_BAD_ARG, "ctx is NULL");
+        SALG_REQUIRE(cls >= 0 && cls < PROF_NCLS, SALG_ERR_BAD_ARG, "bad profiling class");
+        prof_collect(c);
+        if (ms) *ms = c->prof_ms[cls];
+        if (launches) *launches = c->prof_launches[cls];
+        if (bytes) *bytes = c->prof_bytes[cls];
+    });
+}
+
+}  // extern "C"

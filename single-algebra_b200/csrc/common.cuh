@@ -1,0 +1,267 @@
+// common.cuh — internal declarations shared by the translation units of libsalg_b200.so.
+// Not part of the public ABI (that is include/salg.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <nccl.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/salg.h"
+
+namespace salg {
+
+constexpr int LP = 64;  // padded panel width: every dense panel is (rows x 64), row-major, ld = 64
+constexpr int SPMM_CHUNK = 256;          // stored entries per warp work item in the SpMM kernels
+constexpr int GRAM_BUF = LP * LP + LP;   // Gram (64x64) followed by the panel's column sums (64), f64
+
+// ---- errors ------------------------------------------------------------------------------------
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+void set_last_error(const std::string& msg);
+
+#define SALG_CUDA(expr)                                                                         \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess)                                                                  \
+            throw ::salg::Error(_e == cudaErrorMemoryAllocation ? SALG_ERR_OOM : SALG_ERR_CUDA, \
+                                std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " + \
+                                    __FILE__ + ":" + std::to_string(__LINE__) + " (" #expr ")"); \
+    } while (0)
+
+#define SALG_NCCL(expr)                                                                          \
+    do {                                                                                         \
+        ncclResult_t _r = (expr);                                                                \
+        if (_r != ncclSuccess)                                                                   \
+            throw ::salg::Error(SALG_ERR_NCCL, std::string("NCCL error: ") +                     \
+                                                   ncclGetErrorString(_r) + " at " + __FILE__ + \
+                                                   ":" + std::to_string(__LINE__));              \
+    } while (0)
+
+#define SALG_REQUIRE(cond, code, msg)                      \
+    do {                                                   \
+        if (!(cond)) throw ::salg::Error((code), (msg));   \
+    } while (0)
+
+// Wraps the body of every extern "C" entry point: no exception crosses the ABI.
+template <typename F>
+int guarded(F&& f) {
+    try {
+        f();
+        return SALG_OK;
+    } catch (const Error& e) {
+        set_last_error(e.what());
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        set_last_error("host allocation failed");
+        return SALG_ERR_OOM;
+    } catch (const std::exception& e) {
+        set_last_error(e.what());
+        return SALG_ERR_BAD_ARG;
+    } catch (...) {
+        set_last_error("unknown error");
+        return SALG_ERR_BAD_ARG;
+    }
+}
+
+// ---- profiling classes ---------------------------------------------------------------------------
+enum ProfClass {
+    PROF_SPMM = 0,     // Y = A X   (gather over the CSR)
+    PROF_SPMMT,        // Z = A^T Y (gather over the transposed copy)
+    PROF_GRAM,
+    PROF_CHOL,
+    PROF_PANELMUL,
+    PROF_JACOBI,
+    PROF_STATS,
+    PROF_TRANSPOSE,
+    PROF_COMPACT,
+    PROF_ELEMENTWISE,
+    PROF_ALLREDUCE,
+    PROF_H2D,
+    PROF_SPMV,
+    PROF_OTHER,
+    PROF_NCLS
+};
+
+struct ProfRecord {
+    int cls;
+    cudaEvent_t e0, e1;
+    double bytes;
+};
+
+}  // namespace salg
+
+// ---- opaque handle definitions ---------------------------------------------------------------------
+struct salg_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    int rank = 0, nranks = 1;
+    ncclComm_t comm = nullptr;
+    int64_t n_launch = 0;          // kernels of this library launched on `stream` (bench.py: gpu_launches)
+    cudaEvent_t timer0 = nullptr, timer1 = nullptr;
+    // profiling
+    bool prof_on = false;
+    std::vector<salg::ProfRecord> prof_pending;
+    std::vector<cudaEvent_t> event_pool;
+    double prof_ms[salg::PROF_NCLS] = {0};
+    int64_t prof_launches[salg::PROF_NCLS] = {0};
+    double prof_bytes[salg::PROF_NCLS] = {0};
+    // pinned staging ring for uploads
+    static constexpr int N_STAGE = 3;
+    void* stage[N_STAGE] = {nullptr, nullptr, nullptr};
+    cudaEvent_t stage_ev[N_STAGE] = {nullptr, nullptr, nullptr};
+    size_t stage_bytes = 0;
+};
+
+struct salg_csr {
+    salg_ctx* ctx = nullptr;
+    int dtype = SALG_F32;
+    int64_t nrows = 0, ncols = 0, nnz = 0;
+    int64_t* row_ptr = nullptr;  // [nrows+1]
+    uint32_t* col = nullptr;     // [nnz]
+    void* val = nullptr;         // [nnz] of T
+    // lazily built transposed copy (CSR of A^T == CSC of A); invalidated when values change
+    mutable bool t_valid = false;
+    mutable int64_t* t_ptr = nullptr;  // [ncols+1]
+    mutable uint32_t* t_idx = nullptr; // [nnz] row ids, ascending within a column
+    mutable void* t_val = nullptr;     // [nnz]
+    // SpMM work decomposition: row holding the first entry of every SPMM_CHUNK-sized chunk
+    mutable uint32_t* chunk_row = nullptr;
+    mutable uint32_t* t_chunk_row = nullptr;
+};
+
+struct salg_pca {
+    salg_ctx* ctx = nullptr;
+    int dtype = SALG_F32;
+    int64_t d = 0, n_eff = 0, ncols = 0, n_fit_rows_local = 0, n_samples = 0;
+    bool center = true;
+    bool masked = false;
+    std::vector<uint8_t> mask;          // full length (masked models)
+    std::vector<double> singular_values, explained_variance, mean_full;
+    double total_var = 0.0;
+    int numeric_flag = 0;
+    void* d_V = nullptr;      // device panel n_eff x 64 of T: column i = component i (sign-flipped)
+    void* d_mean = nullptr;   // device T[n_eff] mean of the kept columns (zeros when !center)
+    void* d_scores = nullptr; // device n_fit_rows_local x 64 of T (U*S) when keep_scores
+    void* d_tscores = nullptr; int64_t tscores_rows = 0;   // last transform_device result
+    std::vector<double> col_nnz_kept;   // per kept column stored-entry count (REFERENCE_COMPAT unmasked)
+};
+
+namespace salg {
+
+// ---- stream-ordered temporary buffers ------------------------------------------------------------
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaStream_t s = nullptr;
+    DevBuf() = default;
+    DevBuf(size_t n_, cudaStream_t s_) { alloc(n_, s_); }
+    void alloc(size_t n_, cudaStream_t s_) {
+        release();
+        n = n_;
+        s = s_;
+        if (n) SALG_CUDA(cudaMallocAsync((void**)&p, n * sizeof(T), s));
+    }
+    void release() {
+        if (p) cudaFreeAsync(p, s);
+        p = nullptr;
+        n = 0;
+    }
+    ~DevBuf() { release(); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), s(o.s) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) { release(); p = o.p; n = o.n; s = o.s; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    T* get() const { return p; }
+};
+
+// RAII profiling scope: records an event pair around the launches issued inside it.
+struct ProfScope {
+    salg_ctx* ctx;
+    int idx = -1;
+    ProfScope(salg_ctx* c, int cls, double bytes);
+    ~ProfScope();
+};
+void prof_collect(salg_ctx* ctx);  // drains pending events into the per-class totals (syncs)
+
+template <typename T> struct dtype_of;
+template <> struct dtype_of<float> { static constexpr int value = SALG_F32; };
+template <> struct dtype_of<double> { static constexpr int value = SALG_F64; };
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- csr.cu ---------------------------------------------------------------------------------------
+salg_csr* csr_alloc(salg_ctx* ctx, int dtype, int64_t nrows, int64_t ncols, int64_t nnz);
+void csr_destroy(salg_csr* c);
+void csr_invalidate_transpose(const salg_csr* c);   // call with the stream idle (frees device memory)
+template <typename T> void csr_ensure_transpose(salg_ctx* ctx, const salg_csr* c);
+template <typename T> salg_csr* csr_select_columns(salg_ctx* ctx, const salg_csr* c, const uint8_t* mask_host);
+void exclusive_scan_i64(salg_ctx* ctx, const int64_t* in, int64_t* out, int64_t n);
+
+// ---- stats.cu -------------------------------------------------------------------------------------
+// column sums / sums of squares / stored-entry counts in f64 on the device (zeroed here; all-reduced
+// over the ranks of a row-sharded context)
+template <typename T> void col_stats_device(salg_ctx* ctx, const salg_csr* c, double* d_sum, double* d_sumsq, double* d_cnt);
+template <typename T> void sum_row_device(salg_ctx* ctx, const salg_csr* c, T* d_out);
+int64_t global_nrows(salg_ctx* ctx, int64_t local_rows);
+
+// ---- spmm.cu --------------------------------------------------------------------------------------
+// out(nr x 64) = S * X(nc x 64) - alpha * corr^T, S given as CSR arrays (nr rows); val == nullptr => all
+// stored values are 1 (pattern product); alpha: per-row T (nullptr => 1), corr: 64 doubles (nullptr => 0).
+template <typename T>
+void spmm_launch(salg_ctx* ctx, int prof_cls, const int64_t* ptr, const uint32_t* idx, const T* val,
+                 const uint32_t* chunk_row, int64_t nr, int64_t nc, int64_t nnz, const T* X, T* out,
+                 const T* alpha, const double* corr);
+uint32_t* build_chunk_rows(salg_ctx* ctx, const int64_t* ptr, int64_t nr, int64_t nnz);
+// out(nrows x 64) = A X - 1 corr^T
+template <typename T> void spmm_A(salg_ctx* ctx, const salg_csr* c, const T* X, T* out, const double* corr, bool pattern);
+// out(ncols x 64) = A^T Y - mu corr^T  (gather over the transposed copy; local rows only)
+template <typename T> void spmm_At(salg_ctx* ctx, const salg_csr* c, const T* Y, T* out, const T* mu, const double* corr);
+
+// ---- dense.cu -------------------------------------------------------------------------------------
+template <typename T> void panel_gram(salg_ctx* ctx, const T* P, int64_t m, double* d_out /*GRAM_BUF*/);
+template <typename T> void chol_inv(salg_ctx* ctx, const double* d_G, int k, double* d_R, double* d_Rinv, T* d_RinvT, int* d_flag);
+template <typename T> void panel_mul(salg_ctx* ctx, const T* P, int64_t m, const T* d_M /*64x64 row-major*/, T* out);
+void mat64_mul(salg_ctx* ctx, const double* A, const double* B, double* C);  // C = A*B, 64x64 f64
+void vec64_mat(salg_ctx* ctx, const double* v, const double* M, double* o);  // o = v*M
+void jacobi_svd64(salg_ctx* ctx, const double* d_A, int k, double* d_U, double* d_S, double* d_V, int* d_flag);
+template <typename T> void cast_mat64(salg_ctx* ctx, const double* src, T* dst, const double* colscale);
+template <typename T> void panel_colsum(salg_ctx* ctx, const T* P, int64_t m, const T* w, double* d_out64);
+template <typename T> void flip_find(salg_ctx* ctx, const T* V, int64_t n_eff, double* d_sign64);
+template <typename T> void panel_colscale(salg_ctx* ctx, T* P, int64_t m, const double* d_scale64);
+template <typename T> void panel_to_rowmajor_t(salg_ctx* ctx, const T* V, int64_t n, int d, T* out /* d x n */);
+template <typename T> void panel_pack(salg_ctx* ctx, const T* src, int64_t m, int k, T* dst);      // (m x k) -> (m x 64) zero padded
+template <typename T> void panel_unpack(salg_ctx* ctx, const T* src, int64_t m, int k, T* dst);    // (m x 64) -> (m x k)
+template <typename T> void cholqr2(salg_ctx* ctx, T* Y, int64_t m_local, int k, bool sharded, double* d_colsum64,
+                                   double* d_Rtot, int* d_flag, int passes);
+
+void allreduce_f64(salg_ctx* ctx, double* buf, size_t n);
+template <typename T> void allreduce_T(salg_ctx* ctx, T* buf, size_t n);
+
+// ---- pca.cu ---------------------------------------------------------------------------------------
+void mul64_kernel_launch(salg_ctx* ctx, const double* a, const double* b, double* o);   // o = a .* b (64)
+// all-reduce of the per-rank partials of A^T Y - mu cs^T (restores the single rank-1 correction)
+template <typename T> void allreduce_panel_T(salg_ctx* ctx, T* Z, size_t n, const T* mu, const double* cs, int64_t n_eff);
+
+// ---- lanczos.cu -----------------------------------------------------------------------------------
+// Golub-Kahan-Lanczos with full reorthogonalisation on the UNCENTRED operator.
+// Returns d (<= k) converged-or-best triplets: d_V panel (n_eff x 64, column i = right vector i), s.
+template <typename T>
+int lanczos_svd(salg_ctx* ctx, const salg_csr* op, int k, int max_steps, uint64_t seed, double tol, T* d_Vpanel,
+                std::vector<double>& s_out, int* steps_out);
+
+}  // namespace salg

@@ -1,0 +1,331 @@
+// stats.cu — MatrixSum::sum_col / sum_col_squared (src/sparse/csr.rs:259-312, 558-608) fused into ONE
+// pass over the CSR, plus the per-column stored-entry count (MatrixNonZero::nonzero_col,
+// csr.rs:23-64) and MatrixSum::sum_row (csr.rs:314-392).
+//
+// Column statistics are a scatter.  Each CTA privatises the accumulators of a column tile in shared
+// memory (native shared-memory f32 atomics; f64 for f64 matrices), streams its share of the entries
+// with 128-bit loads and flushes the tile once with f64 global atomics, so the HBM stream is the
+// only large traffic: algorithmic bytes = nnz*(S+I) + 2*ncols*S  (SURVEY §8d).
+#include "common.cuh"
+
+namespace salg {
+
+template <typename A>
+__device__ __forceinline__ void smem_add(A* p, A v) { atomicAdd(p, v); }
+
+// ---- variant 1: the whole column range fits one shared-memory tile: flat stream over the entries ------
+template <typename T, typename A, bool CNT>
+__global__ void __launch_bounds__(1024, 1)
+col_stats_flat_kernel(const uint32_t* __restrict__ col, const T* __restrict__ val, int64_t nnz, int ncols,
+                      double* __restrict__ g_sum, double* __restrict__ g_sumsq, double* __restrict__ g_cnt) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    A* acc = reinterpret_cast<A*>(smem_raw);                      // [2*ncols]: sum, sumsq interleaved
+    unsigned* cnt = reinterpret_cast<unsigned*>(acc + 2 * (size_t)ncols);  // [ncols] when CNT
+    for (int i = threadIdx.x; i < 2 * ncols; i += blockDim.x) acc[i] = A(0);
+    if (CNT) for (int i = threadIdx.x; i < ncols; i += blockDim.x) cnt[i] = 0u;
+    __syncthreads();
+
+    // contiguous chunk per CTA, 4 entries per thread per step (the arrays carry 16 entries of slack)
+    int64_t n4 = (nnz + 3) >> 2;
+    int64_t per = (n4 + gridDim.x - 1) / gridDim.x;
+    int64_t b0 = (int64_t)blockIdx.x * per, b1 = b0 + per;
+    if (b1 > n4) b1 = n4;
+    const uint4* col4 = reinterpret_cast<const uint4*>(col);
+    for (int64_t i = b0 + threadIdx.x; i < b1; i += blockDim.x) {
+        uint4 c = __ldcs(col4 + i);
+        T v[4];
+        if (sizeof(T) == 4) {
+            float4 f = __ldcs(reinterpret_cast<const float4*>(val) + i);
+            v[0] = (T)f.x; v[1] = (T)f.y; v[2] = (T)f.z; v[3] = (T)f.w;
+        } else {
+            double2 d0 = __ldcs(reinterpret_cast<const double2*>(val) + 2 * i);
+            double2 d1 = __ldcs(reinterpret_cast<const double2*>(val) + 2 * i + 1);
+            v[0] = (T)d0.x; v[1] = (T)d0.y; v[2] = (T)d1.x; v[3] = (T)d1.y;
+        }
+        uint32_t cc[4] = {c.x, c.y, c.z, c.w};
+        int64_t e = i << 2;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (e + k < nnz) {
+                A x = (A)v[k];
+                smem_add(&acc[2 * cc[k]], x);
+                smem_add(&acc[2 * cc[k] + 1], x * x);
+                if (CNT) atomicAdd(&cnt[cc[k]], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < ncols; i += blockDim.x) {
+        A s = acc[2 * i], q = acc[2 * i + 1];
+        if (s != A(0) || q != A(0)) {
+            atomicAdd(&g_sum[i], (double)s);
+            if (g_sumsq) atomicAdd(&g_sumsq[i], (double)q);
+        }
+        if (CNT) {
+            unsigned n = cnt[i];
+            if (n) atomicAdd(&g_cnt[i], (double)n);
+        }
+    }
+}
+
+// ---- variant 2: column tiles; CTA (tile, row block) touches only its tile's slice of every row ----------
+__device__ __forceinline__ int64_t lower_bound_col(const uint32_t* __restrict__ col, int64_t lo, int64_t hi,
+                                                   uint32_t key) {
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (col[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+template <typename T, typename A, bool CNT>
+__global__ void __launch_bounds__(1024, 1)
+col_stats_tiled_kernel(const int64_t* __restrict__ ptr, const uint32_t* __restrict__ col, const T* __restrict__ val,
+                       int64_t nrows, int ncols, int tile_cols, int n_tiles, double* __restrict__ g_sum,
+                       double* __restrict__ g_sumsq, double* __restrict__ g_cnt) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    A* acc = reinterpret_cast<A*>(smem_raw);
+    unsigned* cnt = reinterpret_cast<unsigned*>(acc + 2 * (size_t)tile_cols);
+    int tile = blockIdx.x % n_tiles;
+    int rb = blockIdx.x / n_tiles, n_rb = gridDim.x / n_tiles;
+    uint32_t c0 = (uint32_t)tile * tile_cols;
+    uint32_t c1 = c0 + tile_cols < (uint32_t)ncols ? c0 + tile_cols : (uint32_t)ncols;
+    for (int i = threadIdx.x; i < 2 * tile_cols; i += blockDim.x) acc[i] = A(0);
+    if (CNT) for (int i = threadIdx.x; i < tile_cols; i += blockDim.x) cnt[i] = 0u;
+    __syncthreads();
+    int64_t per = (nrows + n_rb - 1) / n_rb;
+    int64_t r0 = (int64_t)rb * per, r1 = r0 + per < nrows ? r0 + per : nrows;
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int64_t r = r0 + warp; r < r1; r += nwarp) {
+        int64_t s = ptr[r], e = ptr[r + 1];
+        if (n_tiles > 1) {
+            int64_t lo = lower_bound_col(col, s, e, c0);
+            e = (c1 >= (uint32_t)ncols) ? e : lower_bound_col(col, lo, e, c1);
+            s = lo;
+        }
+        for (int64_t p = s + lane; p < e; p += 32) {
+            uint32_t c = col[p] - c0;
+            A x = (A)val[p];
+            smem_add(&acc[2 * c], x);
+            smem_add(&acc[2 * c + 1], x * x);
+            if (CNT) atomicAdd(&cnt[c], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < (int)(c1 - c0); i += blockDim.x) {
+        A s = acc[2 * i], q = acc[2 * i + 1];
+        if (s != A(0) || q != A(0)) {
+            atomicAdd(&g_sum[c0 + i], (double)s);
+            if (g_sumsq) atomicAdd(&g_sumsq[c0 + i], (double)q);
+        }
+        if (CNT) {
+            unsigned n = cnt[i];
+            if (n) atomicAdd(&g_cnt[c0 + i], (double)n);
+        }
+    }
+}
+
+template <typename T, typename A, bool CNT>
+static void col_stats_launch(salg_ctx* ctx, const salg_csr* c, double* d_sum, double* d_sumsq, double* d_cnt) {
+    cudaStream_t st = ctx->stream;
+    const size_t kMaxSmem = 200 * 1024;
+    size_t per_col = 2 * sizeof(A) + (CNT ? 4 : 0);
+    int ncols = (int)c->ncols;
+    size_t need = per_col * (size_t)ncols;
+    if (need <= kMaxSmem) {
+        auto k = col_stats_flat_kernel<T, A, CNT>;
+        SALG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+        int64_t n4 = (c->nnz + 3) / 4;
+        int grid = (int)(n4 < (int64_t)ctx->sm_count * 1024 ? ceil_div(n4 > 0 ? n4 : 1, 1024) : ctx->sm_count);
+        k<<<grid, 1024, need, st>>>(c->col, (const T*)c->val, c->nnz, ncols, d_sum, d_sumsq, d_cnt);
+        ctx->n_launch++;
+    } else {
+        int tile_cols = (int)(kMaxSmem / per_col);
+        int n_tiles = (int)ceil_div(ncols, tile_cols);
+        tile_cols = (int)ceil_div(ncols, n_tiles);  // balance the tiles
+        int n_rb = ctx->sm_count / n_tiles;
+        if (n_rb < 1) n_rb = 1;
+        if ((int64_t)n_rb > c->nrows) n_rb = (int)(c->nrows > 0 ? c->nrows : 1);
+        auto k = col_stats_tiled_kernel<T, A, CNT>;
+        SALG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+        k<<<n_rb * n_tiles, 1024, per_col * (size_t)tile_cols, st>>>(c->row_ptr, c->col, (const T*)c->val, c->nrows,
+                                                                     ncols, tile_cols, n_tiles, d_sum, d_sumsq, d_cnt);
+        ctx->n_launch++;
+    }
+    SALG_CUDA(cudaGetLastError());
+}
+
+template <typename T>
+void col_stats_device(salg_ctx* ctx, const salg_csr* c, double* d_sum, double* d_sumsq, double* d_cnt) {
+    cudaStream_t st = ctx->stream;
+    int64_t ncols = c->ncols;
+    if (ncols == 0) return;
+    SALG_CUDA(cudaMemsetAsync(d_sum, 0, (size_t)ncols * 8, st));
+    if (d_sumsq) SALG_CUDA(cudaMemsetAsync(d_sumsq, 0, (size_t)ncols * 8, st));
+    if (d_cnt) SALG_CUDA(cudaMemsetAsync(d_cnt, 0, (size_t)ncols * 8, st));
+    if (c->nnz > 0) {
+        ProfScope ps(ctx, PROF_STATS, (double)c->nnz * (sizeof(T) + 4) + 2.0 * (double)ncols * sizeof(T));
+        // f32 matrices accumulate per-CTA partials in f32 (exact for integer counts below 2^24 per CTA
+        // chunk), f64 matrices in f64; the cross-CTA reduction is always f64.
+        if (sizeof(T) == 4) {
+            if (d_cnt) col_stats_launch<T, float, true>(ctx, c, d_sum, d_sumsq, d_cnt);
+            else col_stats_launch<T, float, false>(ctx, c, d_sum, d_sumsq, d_cnt);
+        } else {
+            if (d_cnt) col_stats_launch<T, double, true>(ctx, c, d_sum, d_sumsq, d_cnt);
+            else col_stats_launch<T, double, false>(ctx, c, d_sum, d_sumsq, d_cnt);
+        }
+    }
+    // row-sharded context: global column sums
+    allreduce_f64(ctx, d_sum, (size_t)ncols);
+    if (d_sumsq) allreduce_f64(ctx, d_sumsq, (size_t)ncols);
+    if (d_cnt) allreduce_f64(ctx, d_cnt, (size_t)ncols);
+}
+template void col_stats_device<float>(salg_ctx*, const salg_csr*, double*, double*, double*);
+template void col_stats_device<double>(salg_ctx*, const salg_csr*, double*, double*, double*);
+
+// ---- sum_row ----------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void sum_row_kernel(const int64_t* __restrict__ ptr, const T* __restrict__ val, int64_t nrows,
+                               T* __restrict__ out) {
+    int lane = threadIdx.x & 31;
+    int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = w; r < nrows; r += nw) {
+        int64_t s = ptr[r], e = ptr[r + 1];
+        double a = 0.0;
+        for (int64_t p = s + lane; p < e; p += 32) a += (double)__ldcs(val + p);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
+        if (lane == 0) out[r] = (T)a;
+    }
+}
+
+template <typename T>
+void sum_row_device(salg_ctx* ctx, const salg_csr* c, T* d_out) {
+    if (c->nrows == 0) return;
+    ProfScope ps(ctx, PROF_STATS, (double)c->nnz * sizeof(T) + (double)(c->nrows + 1) * 8 + (double)c->nrows * sizeof(T));
+    int64_t want = ceil_div(c->nrows * 32, 256);
+    int64_t cap = (int64_t)ctx->sm_count * 16;
+    sum_row_kernel<T><<<(unsigned)(want < cap ? want : cap), 256, 0, ctx->stream>>>(c->row_ptr, (const T*)c->val,
+                                                                                    c->nrows, d_out);
+    ctx->n_launch++;
+    SALG_CUDA(cudaGetLastError());
+}
+template void sum_row_device<float>(salg_ctx*, const salg_csr*, float*);
+template void sum_row_device<double>(salg_ctx*, const salg_csr*, double*);
+
+template <typename T>
+__global__ void cast_from_f64_kernel(const double* __restrict__ src, T* __restrict__ dst, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (T)src[i];
+}
+
+template <typename T>
+static void sum_col_api(salg_ctx* ctx, const salg_csr* c, T* sum, T* sumsq) {
+    SALG_REQUIRE(ctx && c, SALG_ERR_BAD_ARG, "ctx/csr is NULL");
+    SALG_REQUIRE(sum, SALG_ERR_BAD_ARG, "sum is NULL");
+    SALG_REQUIRE(c->dtype == dtype_of<T>::value, SALG_ERR_BAD_ARG, "csr value type does not match the entry point");
+    SALG_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    int64_t n = c->ncols;
+    if (n == 0) return;
+    DevBuf<double> d_sum((size_t)n, st), d_sq((size_t)(sumsq ? n : 0), st);
+    col_stats_device<T>(ctx, c, d_sum.get(), sumsq ? d_sq.get() : nullptr, nullptr);
+    DevBuf<T> o((size_t)n, st);
+    cast_from_f64_kernel<T><<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(d_sum.get(), o.get(), n);
+    ctx->n_launch++;
+    SALG_CUDA(cudaMemcpyAsync(sum, o.get(), (size_t)n * sizeof(T), cudaMemcpyDeviceToHost, st));
+    if (sumsq) {
+        SALG_CUDA(cudaStreamSynchronize(st));
+        cast_from_f64_kernel<T><<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(d_sq.get(), o.get(), n);
+        ctx->n_launch++;
+        SALG_CUDA(cudaMemcpyAsync(sumsq, o.get(), (size_t)n * sizeof(T), cudaMemcpyDeviceToHost, st));
+    }
+    SALG_CUDA(cudaGetLastError());
+    SALG_CUDA(cudaStreamSynchronize(st));
+}
+
+template <typename T>
+static void sum_row_api(salg_ctx* ctx, const salg_csr* c, T* out) {
+    SALG_REQUIRE(ctx && c, SALG_ERR_BAD_ARG, "ctx/csr is NULL");
+    SALG_REQUIRE(out || c->nrows == 0, SALG_ERR_BAD_ARG, "out is NULL");
+    SALG_REQUIRE(c->dtype == dtype_of<T>::value, SALG_ERR_BAD_ARG, "csr value type does not match the entry point");
+    SALG_CUDA(cudaSetDevice(ctx->device));
+    if (c->nrows == 0) return;
+    DevBuf<T> o((size_t)c->nrows, ctx->stream);
+    sum_row_device<T>(ctx, c, o.get());
+    SALG_CUDA(cudaMemcpyAsync(out, o.get(), (size_t)c->nrows * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    SALG_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+__global__ void var_col_kernel(const double* __restrict__ sum, const double* __restrict__ sumsq, double n_rows,
+                               double* __restrict__ var, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // MatrixVariance::var_col (src/sparse/csr.rs:649-657): (sumsq/n - mean^2) * n/(n-1)
+    double mean = sum[i] / n_rows;
+    double v = sumsq[i] / n_rows - mean * mean;
+    var[i] = n_rows > 1.0 ? v * (n_rows / (n_rows - 1.0)) : v;
+}
+
+int64_t global_nrows(salg_ctx* ctx, int64_t local_rows) {
+    if (ctx->nranks <= 1) return local_rows;
+    DevBuf<double> d(1, ctx->stream);
+    double h = (double)local_rows;
+    SALG_CUDA(cudaMemcpyAsync(d.get(), &h, 8, cudaMemcpyHostToDevice, ctx->stream));
+    allreduce_f64(ctx, d.get(), 1);
+    SALG_CUDA(cudaMemcpyAsync(&h, d.get(), 8, cudaMemcpyDeviceToHost, ctx->stream));
+    SALG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return (int64_t)(h + 0.5);
+}
+
+}  // namespace salg
+
+using namespace salg;
+
+extern "C" {
+
+int salg_sum_col_f32(salg_ctx* ctx, const salg_csr* c, float* sum, float* sumsq) {
+    return guarded([&] { sum_col_api<float>(ctx, c, sum, sumsq); });
+}
+int salg_sum_col_f64(salg_ctx* ctx, const salg_csr* c, double* sum, double* sumsq) {
+    return guarded([&] { sum_col_api<double>(ctx, c, sum, sumsq); });
+}
+int salg_sum_row_f32(salg_ctx* ctx, const salg_csr* c, float* out) {
+    return guarded([&] { sum_row_api<float>(ctx, c, out); });
+}
+int salg_sum_row_f64(salg_ctx* ctx, const salg_csr* c, double* out) {
+    return guarded([&] { sum_row_api<double>(ctx, c, out); });
+}
+
+int salg_col_stats_f64(salg_ctx* ctx, const salg_csr* c, double* sum, double* sumsq, double* nnz_col,
+                       double* var_col) {
+    return guarded([&] {
+        SALG_REQUIRE(ctx && c, SALG_ERR_BAD_ARG, "ctx/csr is NULL");
+        SALG_CUDA(cudaSetDevice(ctx->device));
+        cudaStream_t st = ctx->stream;
+        int64_t n = c->ncols;
+        if (n == 0) return;
+        DevBuf<double> d_sum((size_t)n, st), d_sq((size_t)n, st), d_cnt((size_t)(nnz_col ? n : 0), st);
+        if (c->dtype == SALG_F64)
+            col_stats_device<double>(ctx, c, d_sum.get(), d_sq.get(), nnz_col ? d_cnt.get() : nullptr);
+        else
+            col_stats_device<float>(ctx, c, d_sum.get(), d_sq.get(), nnz_col ? d_cnt.get() : nullptr);
+        if (sum) SALG_CUDA(cudaMemcpyAsync(sum, d_sum.get(), (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+        if (sumsq) SALG_CUDA(cudaMemcpyAsync(sumsq, d_sq.get(), (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+        if (nnz_col) SALG_CUDA(cudaMemcpyAsync(nnz_col, d_cnt.get(), (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+        if (var_col) {
+            int64_t n_rows = global_nrows(ctx, c->nrows);
+            DevBuf<double> d_var((size_t)n, st);
+            var_col_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(d_sum.get(), d_sq.get(), (double)n_rows,
+                                                                       d_var.get(), n);
+            ctx->n_launch++;
+            SALG_CUDA(cudaGetLastError());
+            SALG_CUDA(cudaMemcpyAsync(var_col, d_var.get(), (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+            SALG_CUDA(cudaStreamSynchronize(st));
+        }
+        SALG_CUDA(cudaStreamSynchronize(st));
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,75 @@
+"""Operator-level parity: centred sparse x panel products, CholeskyQR2, the one-CTA Jacobi SVD."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import planted_counts
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_products(A, X, mu, transposed):
+    A = A.astype(np.float64)
+    X = X.astype(np.float64)
+    if not transposed:
+        Y = A @ X
+        return Y - (mu.astype(np.float64) @ X)[None, :] if mu is not None else Y
+    Z = A.T @ X
+    return Z - mu.astype(np.float64)[:, None] * X.sum(axis=0)[None, :] if mu is not None else Z
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float32, 2e-5), (np.float64, 1e-12)])
+@pytest.mark.parametrize("k", [1, 60, 64])
+def test_spmm_matches_oracle(salg, ctx, dtype, tol, k):
+    A = planted_counts(3000, 500, seed=11, dtype=dtype)
+    # ragged structure: empty rows, one very long row (spans several work chunks), empty columns
+    D = A.toarray()
+    D[5] = 0
+    D[17] = np.arange(500) % 7 + 1
+    D[:, 3] = 0
+    D[-1] = 0
+    A = sp.csr_matrix(D.astype(dtype))
+    d = salg.CsrMatrix.from_scipy(A, ctx).to_device()
+    rng = np.random.default_rng(k)
+    mu = np.asarray(A.mean(axis=0)).ravel().astype(dtype)
+    for transposed in (False, True):
+        X = rng.standard_normal((A.shape[0] if transposed else A.shape[1], k)).astype(dtype)
+        for m in (None, mu):
+            got = salg.op_spmm(d, X, mu=m, transposed=transposed)
+            ref = _ref_products(A, X, m, transposed)
+            scale = np.abs(ref).max()
+            assert np.abs(got - ref).max() <= tol * scale, (transposed, m is None)
+
+
+def test_spmm_single_row_and_tiny(salg, ctx):
+    A = sp.csr_matrix(np.array([[0.0, 2.0, 0.0, 1.0]]))
+    d = salg.CsrMatrix.from_scipy(A, ctx).to_device()
+    X = np.arange(8, dtype=np.float64).reshape(4, 2)
+    assert np.allclose(salg.op_spmm(d, X), A @ X)
+    Y = np.array([[3.0, -1.0]])
+    assert np.allclose(salg.op_spmm(d, Y, transposed=True), A.T @ Y)
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float32, 5e-6), (np.float64, 1e-13)])
+def test_cholqr2(salg, ctx, dtype, tol):
+    rng = np.random.default_rng(0)
+    Y = (rng.standard_normal((5000, 60)) @ np.diag(np.logspace(0, 3, 60)) @ rng.standard_normal((60, 60))).astype(dtype)
+    q, r = salg.op_cholqr2(Y, ctx)
+    assert np.abs(q.astype(np.float64).T @ q.astype(np.float64) - np.eye(60)).max() < tol * 10
+    assert np.abs(q.astype(np.float64) @ r - Y).max() < tol * np.abs(Y).max() * 10
+    assert np.allclose(r, np.triu(r))
+    # same column space as Householder QR
+    qh, _ = np.linalg.qr(Y.astype(np.float64))
+    assert np.abs(qh @ (qh.T @ q) - q).max() < tol * 100
+
+
+@pytest.mark.parametrize("k", [1, 7, 60, 64])
+def test_small_svd_matches_lapack(salg, ctx, k):
+    rng = np.random.default_rng(k)
+    a = rng.standard_normal((k, k)) @ np.diag(np.logspace(0, -6, k)) @ rng.standard_normal((k, k))
+    u, s, vt = salg.op_small_svd(a, ctx)
+    sr = np.linalg.svd(a, compute_uv=False)
+    assert np.max(np.abs(s - sr) / sr[0]) < 1e-13
+    assert np.all(np.diff(s) <= 0)
+    assert np.abs(u @ np.diag(s) @ vt - a).max() < 1e-12 * np.abs(a).max()
+    assert np.abs(u.T @ u - np.eye(k)).max() < 1e-10 and np.abs(vt @ vt.T - np.eye(k)).max() < 1e-10
