@@ -261,7 +261,7 @@ def run_ours(args, wl):
     if dom:
         tms, n, b = prof[dom]
         achieved = b / tms / 1e6     # GB/s
-        roofline = {"bound": "hbm", "kernel": "spmm_chunk_kernel<float> (" + ("A^T Y on the transposed copy" if dom == "spmm_t" else "A X") + ")",
+        roofline = {"bound": "hbm", "kernel": ("tc_aty_kernel (A^T Y, tcgen05 tile-densified)" if dom == "spmm_t" else "tc_ax_kernel (A X, tcgen05 tile-densified)"),
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                     "peak_source": peak_src, "avg_launch_ms": tms / n, "launches": n,
                     "algorithmic_bytes_per_launch": b / n, "share_of_step": tms / (ms * 1.0)}
@@ -289,6 +289,8 @@ def run_ours(args, wl):
 
         for _ in range(max(1, min(args.warmup, 2))):
             step_e2e()
+        ctx.prof_reset()
+        ctx.prof_enable(True)
         barrier()
         ctx.sync()
         ctx.timer_start()
@@ -297,11 +299,14 @@ def run_ours(args, wl):
             step_e2e()
         ms2 = ctx.timer_stop()
         barrier()
+        ctx.prof_enable(False)
+        e2e_classes = {k: round(v[0] / max(1, min(args.steps, 3)), 3) for k, v in ctx.prof().items()}
         ms2_step = max_over_ranks(ms2) / k_e2e
         h2d = sum_over_ranks(nnz * 8 + (nloc + 1) * 8 + om.nbytes + (wl["ncols"] if mask is not None else 0))
         d2h = sum_over_ranks(nloc * wl["k"] * 4 + 8 * wl["ncols"] + 16 * wl["k"])
         e2e = {"value": wl["nrows"] / (ms2_step * 1e-3), "unit": "cells/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": ms2_step, "steps": k_e2e}
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": ms2_step, "steps": k_e2e,
+               "class_ms_per_step": e2e_classes}
     elif not args.no_e2e:
         e2e = {"value": None, "unit": "cells/s", "skipped": f"host memory {host_mem_gb():.0f} GB < {need_gb:.0f} GB needed"}
 

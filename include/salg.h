@@ -88,6 +88,9 @@ int salg_ctx_rank(const salg_ctx* ctx, int* rank, int* nranks);
  * start synchronises the stream and records; stop records, waits and returns the elapsed device ms. */
 int salg_timer_start(salg_ctx* ctx);
 int salg_timer_stop(salg_ctx* ctx, double* ms);
+/* Sparse x panel product implementation for f32 operators: 0 = tile-densified tcgen05 kernels (default),
+ * 1 = CUDA-core chunk kernels (always used for f64).  Environment default: SALG_SPMM_IMPL=chunk. */
+int salg_ctx_set_spmm_impl(salg_ctx* ctx, int impl);
 /* Number of kernels of this library launched on the context's stream since its creation. */
 int salg_launch_count(salg_ctx* ctx, int64_t* out);
 

@@ -54,6 +54,7 @@ PROTOTYPES = {
     "salg_ctx_rank": [_P, C.POINTER(_int), C.POINTER(_int)],
     "salg_timer_start": [_P],
     "salg_timer_stop": [_P, C.POINTER(C.c_double)],
+    "salg_ctx_set_spmm_impl": [_P, _int],
     "salg_launch_count": [_P, C.POINTER(_i64)],
     "salg_prof_enable": [_P, _int],
     "salg_prof_reset": [_P],

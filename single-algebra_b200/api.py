@@ -61,6 +61,10 @@ class Context:
         N.check(N.load().salg_timer_stop(self._h, C.byref(ms)))
         return ms.value
 
+    def set_spmm_impl(self, impl: str):
+        """'tc' (tcgen05 tile-densified, default for f32) or 'chunk' (CUDA-core kernels)."""
+        N.check(N.load().salg_ctx_set_spmm_impl(self._h, {'tc': 0, 'chunk': 1}[impl]))
+
     def launch_count(self) -> int:
         n = C.c_int64()
         N.check(N.load().salg_launch_count(self._h, C.byref(n)))

@@ -84,6 +84,10 @@ static salg_ctx* ctx_new(int device) {
     cudaDeviceProp prop;
     SALG_CUDA(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
+    {
+        const char* e = getenv("SALG_SPMM_IMPL");
+        c->spmm_impl = (e && strcmp(e, "chunk") == 0) ? 1 : 0;
+    }
     SALG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     SALG_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     // keep freed temporaries cached in the stream-ordered pool
@@ -232,6 +236,14 @@ int salg_timer_stop(salg_ctx* c, double* ms) {
         float f = 0.f;
         SALG_CUDA(cudaEventElapsedTime(&f, c->timer0, c->timer1));
         *ms = (double)f;
+    });
+}
+
+int salg_ctx_set_spmm_impl(salg_ctx* c, int impl) {
+    return guarded([&] {
+        SALG_REQUIRE(c, SALG_ERR_BAD_ARG, "ctx is NULL");
+        SALG_REQUIRE(impl == 0 || impl == 1, SALG_ERR_BAD_ARG, "impl must be 0 (tcgen05) or 1 (chunk)");
+        c->spmm_impl = impl;
     });
 }
 

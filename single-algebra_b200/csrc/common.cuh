@@ -107,6 +107,7 @@ struct salg_ctx {
     cudaStream_t copy_stream = nullptr;
     int rank = 0, nranks = 1;
     ncclComm_t comm = nullptr;
+    int spmm_impl = 0;             // 0 = tcgen05 tile-densified products for f32 operators, 1 = CUDA-core chunk kernels
     int64_t n_launch = 0;          // kernels of this library launched on `stream` (bench.py: gpu_launches)
     cudaEvent_t timer0 = nullptr, timer1 = nullptr;
     // profiling
@@ -138,6 +139,8 @@ struct salg_csr {
     // SpMM work decomposition: row holding the first entry of every SPMM_CHUNK-sized chunk
     mutable uint32_t* chunk_row = nullptr;
     mutable uint32_t* t_chunk_row = nullptr;
+    // tile-densified format for the tcgen05 products (tc.cu); invalidated when values change
+    mutable void* tc = nullptr;
 };
 
 struct salg_pca {
@@ -231,6 +234,13 @@ uint32_t* build_chunk_rows(salg_ctx* ctx, const int64_t* ptr, int64_t nr, int64_
 template <typename T> void spmm_A(salg_ctx* ctx, const salg_csr* c, const T* X, T* out, const double* corr, bool pattern);
 // out(ncols x 64) = A^T Y - mu corr^T  (gather over the transposed copy; local rows only)
 template <typename T> void spmm_At(salg_ctx* ctx, const salg_csr* c, const T* Y, T* out, const T* mu, const double* corr);
+
+// ---- tc.cu ----------------------------------------------------------------------------------------
+// tile-densified tcgen05 products (f32 operators only).  SALG_SPMM_IMPL=chunk selects the CUDA-core kernels.
+bool tc_enabled(const salg_ctx* ctx);
+void tc_free(void* tiles);
+void tc_spmm_A(salg_ctx* ctx, const salg_csr* c, const float* X, float* Y, const double* corr);
+void tc_spmm_At(salg_ctx* ctx, const salg_csr* c, const float* Y, float* Z, const float* mu, const double* corr);
 
 // ---- dense.cu -------------------------------------------------------------------------------------
 template <typename T> void panel_gram(salg_ctx* ctx, const T* P, int64_t m, double* d_out /*GRAM_BUF*/);

@@ -34,6 +34,8 @@ void csr_invalidate_transpose(const salg_csr* c) {
     if (c->t_idx) cudaFree(c->t_idx);
     if (c->t_val) cudaFree(c->t_val);
     if (c->t_chunk_row) cudaFree(c->t_chunk_row);
+    if (c->tc) tc_free(c->tc);
+    c->tc = nullptr;
     c->t_chunk_row = nullptr;
     c->t_ptr = nullptr;
     c->t_idx = nullptr;

@@ -10,6 +10,8 @@
 // cost the same per warp.  A lane owns two adjacent panel columns; per entry the warp issues ONE coalesced
 // 256 B (f32) / 512 B (f64) panel-row load and 2 FMAs per lane.  Rows completely inside a chunk are stored
 // directly; rows cut by a chunk border are accumulated with atomics onto a pre-initialised output row.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace salg {
@@ -189,6 +191,12 @@ template void spmm_launch<double>(salg_ctx*, int, const int64_t*, const uint32_t
 
 template <typename T>
 void spmm_A(salg_ctx* ctx, const salg_csr* c, const T* X, T* out, const double* corr, bool pattern) {
+    if constexpr (std::is_same<T, float>::value) {
+        if (!pattern && tc_enabled(ctx)) {
+            tc_spmm_A(ctx, c, X, out, corr);
+            return;
+        }
+    }
     if (!c->chunk_row) c->chunk_row = build_chunk_rows(ctx, c->row_ptr, c->nrows, c->nnz);
     spmm_launch<T>(ctx, PROF_SPMM, c->row_ptr, c->col, pattern ? nullptr : (const T*)c->val, c->chunk_row, c->nrows,
                    c->ncols, c->nnz, X, out, nullptr, corr);
@@ -198,6 +206,12 @@ template void spmm_A<double>(salg_ctx*, const salg_csr*, const double*, double*,
 
 template <typename T>
 void spmm_At(salg_ctx* ctx, const salg_csr* c, const T* Y, T* out, const T* mu, const double* corr) {
+    if constexpr (std::is_same<T, float>::value) {
+        if (tc_enabled(ctx)) {
+            tc_spmm_At(ctx, c, Y, out, mu, corr);
+            return;
+        }
+    }
     csr_ensure_transpose<T>(ctx, c);
     if (!c->t_chunk_row) c->t_chunk_row = build_chunk_rows(ctx, c->t_ptr, c->ncols, c->nnz);
     spmm_launch<T>(ctx, PROF_SPMMT, c->t_ptr, c->t_idx, (const T*)c->t_val, c->t_chunk_row, c->ncols, c->nrows, c->nnz,

@@ -73,3 +73,28 @@ def test_small_svd_matches_lapack(salg, ctx, k):
     assert np.all(np.diff(s) <= 0)
     assert np.abs(u @ np.diag(s) @ vt - a).max() < 1e-12 * np.abs(a).max()
     assert np.abs(u.T @ u - np.eye(k)).max() < 1e-10 and np.abs(vt @ vt.T - np.eye(k)).max() < 1e-10
+
+
+def test_tc_products_match_chunk_kernels_and_f64(salg, ctx):
+    """tcgen05 tile-densified products vs the CUDA-core kernels vs f64: exact-bf16 operator (raw counts, one
+    operator term) and a general float operator (three terms), ragged shapes, both products."""
+    rng = np.random.default_rng(5)
+    for make_general in (False, True):
+        A = planted_counts(1000 + 37, 300 + 11, seed=31, dtype=np.float32)      # not multiples of 128 / 64
+        if make_general:
+            A.data = (A.data * (1 + rng.random(A.nnz))).astype(np.float32)
+        d = salg.CsrMatrix.from_scipy(A, ctx).to_device()
+        mu = np.asarray(A.mean(axis=0)).ravel().astype(np.float32)
+        for transposed in (False, True):
+            X = rng.standard_normal((A.shape[0] if transposed else A.shape[1], 60)).astype(np.float32)
+            ref = _ref_products(A, X, mu, transposed)
+            ctx.set_spmm_impl("tc")
+            got_tc = salg.op_spmm(d, X, mu=mu, transposed=transposed)
+            ctx.set_spmm_impl("chunk")
+            got_ch = salg.op_spmm(d, X, mu=mu, transposed=transposed)
+            ctx.set_spmm_impl("tc")
+            scale = np.abs(ref).max()
+            assert np.abs(got_tc - ref).max() <= 2e-5 * scale, (make_general, transposed)
+            assert np.abs(got_ch - ref).max() <= 2e-5 * scale
+            # the split-bf16 tensor-core product is as accurate as the f32 FMA chain
+            assert np.abs(got_tc - ref).max() <= 4 * np.abs(got_ch - ref).max() + 1e-6 * scale
