@@ -279,12 +279,23 @@ def run_ours(args, wl):
         t_sc, sc = pinned_empty(nloc * wl["k"], np.float32)
         dev.free()   # the e2e leg owns device memory from here on
 
+        verbose = bool(os.environ.get("SALG_BENCH_VERBOSE"))
+
         def step_e2e():
+            t0 = time.perf_counter()
             x = s.CsrMatrix(nloc, wl["ncols"], off.view(np.uint64), idx, val, ctx)
+            x.to_device()
+            t1 = time.perf_counter()
             p2 = make_pca()
             out = p2.fit_transform(x, omega=om)
+            t2 = time.perf_counter()
             sc.reshape(nloc, -1)[:] = out        # result lands in host memory (pageable -> pinned copy is host-side)
             x.drop_device()
+            p2._free_model()
+            t3 = time.perf_counter()
+            if verbose and rank == 0:
+                print(f"[e2e] upload {1e3*(t1-t0):.1f} ms, fit_transform+fetch {1e3*(t2-t1):.1f} ms, copy+free {1e3*(t3-t2):.1f} ms",
+                      file=sys.stderr, flush=True)
             return out
 
         for _ in range(max(1, min(args.warmup, 2))):

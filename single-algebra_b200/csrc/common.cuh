@@ -212,13 +212,18 @@ salg_csr* csr_alloc(salg_ctx* ctx, int dtype, int64_t nrows, int64_t ncols, int6
 void csr_destroy(salg_csr* c);
 void csr_invalidate_transpose(const salg_csr* c);   // call with the stream idle (frees device memory)
 template <typename T> void csr_ensure_transpose(salg_ctx* ctx, const salg_csr* c);
-template <typename T> salg_csr* csr_select_columns(salg_ctx* ctx, const salg_csr* c, const uint8_t* mask_host);
+// d_row_kept (optional, [nrows+1]): per-row kept counts already computed by col_stats_device -> skips the count pass
+template <typename T> salg_csr* csr_select_columns(salg_ctx* ctx, const salg_csr* c, const uint8_t* mask_host,
+                                                   int64_t* d_row_kept = nullptr);
 void exclusive_scan_i64(salg_ctx* ctx, const int64_t* in, int64_t* out, int64_t n);
 
 // ---- stats.cu -------------------------------------------------------------------------------------
 // column sums / sums of squares / stored-entry counts in f64 on the device (zeroed here; all-reduced
 // over the ranks of a row-sharded context)
-template <typename T> void col_stats_device(salg_ctx* ctx, const salg_csr* c, double* d_sum, double* d_sumsq, double* d_cnt);
+// keepbits (ncols bits) + row_kept [nrows+1]: also count, per row, the entries in kept columns (the compaction's
+// count pass fused into the statistics pass)
+template <typename T> void col_stats_device(salg_ctx* ctx, const salg_csr* c, double* d_sum, double* d_sumsq, double* d_cnt,
+                                            const uint32_t* keepbits = nullptr, int64_t* row_kept = nullptr);
 template <typename T> void sum_row_device(salg_ctx* ctx, const salg_csr* c, T* d_out);
 int64_t global_nrows(salg_ctx* ctx, int64_t local_rows);
 

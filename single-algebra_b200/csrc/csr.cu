@@ -258,24 +258,31 @@ __global__ void write_kept_kernel(const int64_t* __restrict__ ptr, const uint32_
     for (int64_t r = w; r < nrows; r += nw) {
         int64_t s = ptr[r], e = ptr[r + 1];
         int64_t o = new_ptr[r];
-        for (int64_t base = s; base < e; base += 32) {
-            int64_t p = base + lane;
-            uint32_t m = 0xFFFFFFFFu;
-            if (p < e) m = map[col[p]];
-            bool keep = (m != 0xFFFFFFFFu);
-            unsigned b = __ballot_sync(0xFFFFFFFFu, keep);
-            if (keep) {
-                int64_t q = o + __popc(b & lt);
-                new_col[q] = m;
-                new_val[q] = val[p];
+        for (int64_t base = s; base < e; base += 128) {      // 4 independent index/map loads in flight per lane
+            uint32_t m[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                int64_t p = base + 32 * u + lane;
+                m[u] = (p < e) ? map[__ldcs(col + p)] : 0xFFFFFFFFu;
             }
-            o += __popc(b);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                int64_t p = base + 32 * u + lane;
+                bool keep = (m[u] != 0xFFFFFFFFu);
+                unsigned b = __ballot_sync(0xFFFFFFFFu, keep);
+                if (keep) {
+                    int64_t q = o + __popc(b & lt);
+                    new_col[q] = m[u];
+                    new_val[q] = val[p];
+                }
+                o += __popc(b);
+            }
         }
     }
 }
 
 template <typename T>
-salg_csr* csr_select_columns(salg_ctx* ctx, const salg_csr* c, const uint8_t* mask_host) {
+salg_csr* csr_select_columns(salg_ctx* ctx, const salg_csr* c, const uint8_t* mask_host, int64_t* d_row_kept) {
     cudaStream_t st = ctx->stream;
     int64_t ncols = c->ncols, nrows = c->nrows;
     DevBuf<uint8_t> d_mask((size_t)ncols + 1, st);
@@ -302,11 +309,13 @@ salg_csr* csr_select_columns(salg_ctx* ctx, const salg_csr* c, const uint8_t* ma
     try {
         double bytes = (double)c->nnz * (sizeof(T) + 4) + 2.0 * (double)(nrows + 1) * 8;
         ProfScope ps(ctx, PROF_COMPACT, bytes);
-        count_kept_kernel<<<grid_for(ctx, (nrows + 1) * 32, 256, 8), 256, 0, st>>>(c->row_ptr, c->col, d_map.get(),
-                                                                                   nrows, d_cnt.get());
-        ctx->n_launch++;
-        SALG_CUDA(cudaGetLastError());
-        exclusive_scan_i64(ctx, d_cnt.get(), new_ptr, nrows + 1);
+        if (!d_row_kept) {
+            count_kept_kernel<<<grid_for(ctx, (nrows + 1) * 32, 256, 8), 256, 0, st>>>(c->row_ptr, c->col, d_map.get(),
+                                                                                       nrows, d_cnt.get());
+            ctx->n_launch++;
+            SALG_CUDA(cudaGetLastError());
+        }
+        exclusive_scan_i64(ctx, d_row_kept ? d_row_kept : d_cnt.get(), new_ptr, nrows + 1);
         int64_t nnz_eff = 0;
         SALG_CUDA(cudaMemcpyAsync(&nnz_eff, new_ptr + nrows, 8, cudaMemcpyDeviceToHost, st));
         SALG_CUDA(cudaStreamSynchronize(st));
@@ -335,8 +344,8 @@ salg_csr* csr_select_columns(salg_ctx* ctx, const salg_csr* c, const uint8_t* ma
     }
     return out;
 }
-template salg_csr* csr_select_columns<float>(salg_ctx*, const salg_csr*, const uint8_t*);
-template salg_csr* csr_select_columns<double>(salg_ctx*, const salg_csr*, const uint8_t*);
+template salg_csr* csr_select_columns<float>(salg_ctx*, const salg_csr*, const uint8_t*, int64_t*);
+template salg_csr* csr_select_columns<double>(salg_ctx*, const salg_csr*, const uint8_t*, int64_t*);
 
 // ---- transposed copy ------------------------------------------------------------------------------------
 // CSR of A^T (== CSC of A): stable radix sort of the entries by column id keeps rows ascending inside

@@ -32,18 +32,44 @@ panel_gram_kernel(const T* __restrict__ P, int64_t m, double* __restrict__ out) 
             tile[r][c] = (r0 + r < m) ? P[(r0 + r) * LP + c] : T(0);
         }
         __syncthreads();
-#pragma unroll 4
-        for (int r = 0; r < TR; r++) {
-            double a[4], b[4];
+        if (sizeof(T) == 4) {
+            // f32 panels: 32-row partial products in f32 (relative error <= 32 * 2^-24 per partial), summed in f64
+            float p[4][4];
 #pragma unroll
-            for (int x = 0; x < 4; x++) {
-                a[x] = (double)tile[r][4 * ti + x];
-                b[x] = (double)tile[r][4 * tj + x];
+            for (int x = 0; x < 4; x++)
+#pragma unroll
+                for (int y = 0; y < 4; y++) p[x][y] = 0.f;
+#pragma unroll 8
+            for (int r = 0; r < TR; r++) {
+                float a[4], b[4];
+#pragma unroll
+                for (int x = 0; x < 4; x++) {
+                    a[x] = (float)tile[r][4 * ti + x];
+                    b[x] = (float)tile[r][4 * tj + x];
+                }
+#pragma unroll
+                for (int x = 0; x < 4; x++)
+#pragma unroll
+                    for (int y = 0; y < 4; y++) p[x][y] = fmaf(a[x], b[y], p[x][y]);
             }
 #pragma unroll
             for (int x = 0; x < 4; x++)
 #pragma unroll
-                for (int y = 0; y < 4; y++) acc[x][y] = fma(a[x], b[y], acc[x][y]);
+                for (int y = 0; y < 4; y++) acc[x][y] += (double)p[x][y];
+        } else {
+#pragma unroll 4
+            for (int r = 0; r < TR; r++) {
+                double a[4], b[4];
+#pragma unroll
+                for (int x = 0; x < 4; x++) {
+                    a[x] = (double)tile[r][4 * ti + x];
+                    b[x] = (double)tile[r][4 * tj + x];
+                }
+#pragma unroll
+                for (int x = 0; x < 4; x++)
+#pragma unroll
+                    for (int y = 0; y < 4; y++) acc[x][y] = fma(a[x], b[y], acc[x][y]);
+            }
         }
         if (tid < LP) {
             for (int r = 0; r < TR; r++) cs += (double)tile[r][tid];

@@ -112,7 +112,20 @@ static salg_pca* pca_fit(salg_ctx* ctx, const salg_csr* x, const salg_pca_params
         // ---- column statistics over ALL columns: mean_ and total_var (pca/sparse/mod.rs:106-131,
         //      pca/sparse_masked/mod.rs:275-311) — one pass instead of the reference's three
         DevBuf<double> d_sum((size_t)ncols, st), d_sq((size_t)ncols, st);
-        col_stats_device<T>(ctx, x, d_sum.get(), d_sq.get(), nullptr);
+        DevBuf<int64_t> d_row_kept;
+        if (mask) {
+            // the compaction's count pass rides on the statistics pass (one read of the CSR instead of two)
+            std::vector<uint32_t> bits((size_t)(ncols + 31) / 32, 0u);
+            for (int64_t c = 0; c < ncols; c++)
+                if (mask[c]) bits[c >> 5] |= 1u << (c & 31);
+            DevBuf<uint32_t> d_bits(bits.size(), st);
+            SALG_CUDA(cudaMemcpyAsync(d_bits.get(), bits.data(), bits.size() * 4, cudaMemcpyHostToDevice, st));
+            d_row_kept.alloc((size_t)x->nrows + 1, st);
+            col_stats_device<T>(ctx, x, d_sum.get(), d_sq.get(), nullptr, d_bits.get(), d_row_kept.get());
+            SALG_CUDA(cudaStreamSynchronize(st));
+        } else {
+            col_stats_device<T>(ctx, x, d_sum.get(), d_sq.get(), nullptr);
+        }
         std::vector<double> h_sum((size_t)ncols), h_sq((size_t)ncols);
         SALG_CUDA(cudaMemcpyAsync(h_sum.data(), d_sum.get(), (size_t)ncols * 8, cudaMemcpyDeviceToHost, st));
         SALG_CUDA(cudaMemcpyAsync(h_sq.data(), d_sq.get(), (size_t)ncols * 8, cudaMemcpyDeviceToHost, st));
@@ -142,7 +155,7 @@ static salg_pca* pca_fit(salg_ctx* ctx, const salg_csr* x, const salg_pca_params
         const salg_csr* op = x;
         DevBuf<uint32_t> d_kept;
         if (mask) {
-            compact = csr_select_columns<T>(ctx, x, mask);
+            compact = csr_select_columns<T>(ctx, x, mask, d_row_kept.get());
             op = compact;
             d_kept.alloc((size_t)n_eff, st);
             SALG_CUDA(cudaMemcpyAsync(d_kept.get(), kept.data(), (size_t)n_eff * 4, cudaMemcpyHostToDevice, st));
@@ -193,7 +206,9 @@ static salg_pca* pca_fit(salg_ctx* ctx, const salg_csr* x, const salg_pca_params
             spmm_A<T>(ctx, op, Om.get(), Y.get(), center ? corr.get() : nullptr, false);
             for (int it = 0; it < q; it++) {
                 if (tall_norm) {
-                    cholqr2<T>(ctx, Y.get(), m_loc, l, true, cs.get(), nullptr, d_flag.get(), 2);
+                    // intermediate iterations only need a well-conditioned basis of span(Y) (the subspace does not
+                    // depend on the normaliser): one CholeskyQR pass; the final Q gets two
+                    cholqr2<T>(ctx, Y.get(), m_loc, l, true, cs.get(), nullptr, d_flag.get(), 1);
                 } else if (center) {
                     panel_colsum<T>(ctx, Y.get(), m_loc, nullptr, cs.get());
                     allreduce_f64(ctx, cs.get(), LP);

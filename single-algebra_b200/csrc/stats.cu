@@ -82,16 +82,19 @@ template <typename T, typename A, bool CNT>
 __global__ void __launch_bounds__(1024, 1)
 col_stats_tiled_kernel(const int64_t* __restrict__ ptr, const uint32_t* __restrict__ col, const T* __restrict__ val,
                        int64_t nrows, int ncols, int tile_cols, int n_tiles, double* __restrict__ g_sum,
-                       double* __restrict__ g_sumsq, double* __restrict__ g_cnt) {
+                       double* __restrict__ g_sumsq, double* __restrict__ g_cnt, const uint32_t* __restrict__ keepbits,
+                       unsigned long long* __restrict__ row_kept) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     A* acc = reinterpret_cast<A*>(smem_raw);
     unsigned* cnt = reinterpret_cast<unsigned*>(acc + 2 * (size_t)tile_cols);
+    unsigned* kb = cnt + (CNT ? tile_cols : 0);        // keep-bitmask of the whole column range (fused compaction count)
     int tile = blockIdx.x % n_tiles;
     int rb = blockIdx.x / n_tiles, n_rb = gridDim.x / n_tiles;
     uint32_t c0 = (uint32_t)tile * tile_cols;
     uint32_t c1 = c0 + tile_cols < (uint32_t)ncols ? c0 + tile_cols : (uint32_t)ncols;
     for (int i = threadIdx.x; i < 2 * tile_cols; i += blockDim.x) acc[i] = A(0);
     if (CNT) for (int i = threadIdx.x; i < tile_cols; i += blockDim.x) cnt[i] = 0u;
+    if (keepbits) for (int i = threadIdx.x; i < (ncols + 31) / 32; i += blockDim.x) kb[i] = keepbits[i];
     __syncthreads();
     int64_t per = (nrows + n_rb - 1) / n_rb;
     int64_t r0 = (int64_t)rb * per, r1 = r0 + per < nrows ? r0 + per : nrows;
@@ -103,12 +106,36 @@ col_stats_tiled_kernel(const int64_t* __restrict__ ptr, const uint32_t* __restri
             e = (c1 >= (uint32_t)ncols) ? e : lower_bound_col(col, lo, e, c1);
             s = lo;
         }
-        for (int64_t p = s + lane; p < e; p += 32) {
-            uint32_t c = col[p] - c0;
-            A x = (A)val[p];
-            smem_add(&acc[2 * c], x);
-            smem_add(&acc[2 * c + 1], x * x);
-            if (CNT) atomicAdd(&cnt[c], 1u);
+        int kept = 0;
+        for (int64_t p = s + lane; p < e; p += 128) {      // 4 independent loads in flight per lane
+            uint32_t cc[4];
+            T vv[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                int64_t q = p + 32 * u;
+                bool ok = q < e;
+                cc[u] = ok ? __ldcs(col + q) : 0u;
+                vv[u] = ok ? __ldcs(val + q) : T(0);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (p + 32 * u < e) {
+                    uint32_t c = cc[u] - c0;
+                    A x = (A)vv[u];
+                    smem_add(&acc[2 * c], x);
+                    smem_add(&acc[2 * c + 1], x * x);
+                    if (CNT) atomicAdd(&cnt[c], 1u);
+                    if (keepbits) kept += (kb[cc[u] >> 5] >> (cc[u] & 31)) & 1u;
+                }
+            }
+        }
+        if (keepbits) {
+#pragma unroll
+            for (int o = 16; o; o >>= 1) kept += __shfl_xor_sync(0xFFFFFFFFu, kept, o);
+            if (lane == 0) {
+                if (n_tiles > 1) atomicAdd(&row_kept[r], (unsigned long long)kept);
+                else row_kept[r] = (unsigned long long)kept;
+            }
         }
     }
     __syncthreads();
@@ -126,13 +153,15 @@ col_stats_tiled_kernel(const int64_t* __restrict__ ptr, const uint32_t* __restri
 }
 
 template <typename T, typename A, bool CNT>
-static void col_stats_launch(salg_ctx* ctx, const salg_csr* c, double* d_sum, double* d_sumsq, double* d_cnt) {
+static void col_stats_launch(salg_ctx* ctx, const salg_csr* c, double* d_sum, double* d_sumsq, double* d_cnt,
+                             const uint32_t* keepbits, int64_t* row_kept) {
     cudaStream_t st = ctx->stream;
     const size_t kMaxSmem = 200 * 1024;
     size_t per_col = 2 * sizeof(A) + (CNT ? 4 : 0);
     int ncols = (int)c->ncols;
+    size_t kb_bytes = keepbits ? (size_t)((ncols + 31) / 32) * 4 : 0;
     size_t need = per_col * (size_t)ncols;
-    if (need <= kMaxSmem) {
+    if (need <= kMaxSmem && !keepbits) {
         auto k = col_stats_flat_kernel<T, A, CNT>;
         SALG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
         int64_t n4 = (c->nnz + 3) / 4;
@@ -140,7 +169,7 @@ static void col_stats_launch(salg_ctx* ctx, const salg_csr* c, double* d_sum, do
         k<<<grid, 1024, need, st>>>(c->col, (const T*)c->val, c->nnz, ncols, d_sum, d_sumsq, d_cnt);
         ctx->n_launch++;
     } else {
-        int tile_cols = (int)(kMaxSmem / per_col);
+        int tile_cols = (int)((kMaxSmem - kb_bytes) / per_col);
         int n_tiles = (int)ceil_div(ncols, tile_cols);
         tile_cols = (int)ceil_div(ncols, n_tiles);  // balance the tiles
         int n_rb = ctx->sm_count / n_tiles;
@@ -148,31 +177,35 @@ static void col_stats_launch(salg_ctx* ctx, const salg_csr* c, double* d_sum, do
         if ((int64_t)n_rb > c->nrows) n_rb = (int)(c->nrows > 0 ? c->nrows : 1);
         auto k = col_stats_tiled_kernel<T, A, CNT>;
         SALG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-        k<<<n_rb * n_tiles, 1024, per_col * (size_t)tile_cols, st>>>(c->row_ptr, c->col, (const T*)c->val, c->nrows,
-                                                                     ncols, tile_cols, n_tiles, d_sum, d_sumsq, d_cnt);
+        if (row_kept && n_tiles > 1) SALG_CUDA(cudaMemsetAsync(row_kept, 0, (size_t)(c->nrows + 1) * 8, st));
+        k<<<n_rb * n_tiles, 1024, per_col * (size_t)tile_cols + kb_bytes, st>>>(
+            c->row_ptr, c->col, (const T*)c->val, c->nrows, ncols, tile_cols, n_tiles, d_sum, d_sumsq, d_cnt, keepbits,
+            (unsigned long long*)row_kept);
         ctx->n_launch++;
     }
     SALG_CUDA(cudaGetLastError());
 }
 
 template <typename T>
-void col_stats_device(salg_ctx* ctx, const salg_csr* c, double* d_sum, double* d_sumsq, double* d_cnt) {
+void col_stats_device(salg_ctx* ctx, const salg_csr* c, double* d_sum, double* d_sumsq, double* d_cnt,
+                      const uint32_t* keepbits, int64_t* row_kept) {
     cudaStream_t st = ctx->stream;
     int64_t ncols = c->ncols;
     if (ncols == 0) return;
     SALG_CUDA(cudaMemsetAsync(d_sum, 0, (size_t)ncols * 8, st));
     if (d_sumsq) SALG_CUDA(cudaMemsetAsync(d_sumsq, 0, (size_t)ncols * 8, st));
     if (d_cnt) SALG_CUDA(cudaMemsetAsync(d_cnt, 0, (size_t)ncols * 8, st));
+    if (row_kept) SALG_CUDA(cudaMemsetAsync(row_kept, 0, (size_t)(c->nrows + 1) * 8, st));
     if (c->nnz > 0) {
         ProfScope ps(ctx, PROF_STATS, (double)c->nnz * (sizeof(T) + 4) + 2.0 * (double)ncols * sizeof(T));
         // f32 matrices accumulate per-CTA partials in f32 (exact for integer counts below 2^24 per CTA
         // chunk), f64 matrices in f64; the cross-CTA reduction is always f64.
         if (sizeof(T) == 4) {
-            if (d_cnt) col_stats_launch<T, float, true>(ctx, c, d_sum, d_sumsq, d_cnt);
-            else col_stats_launch<T, float, false>(ctx, c, d_sum, d_sumsq, d_cnt);
+            if (d_cnt) col_stats_launch<T, float, true>(ctx, c, d_sum, d_sumsq, d_cnt, keepbits, row_kept);
+            else col_stats_launch<T, float, false>(ctx, c, d_sum, d_sumsq, d_cnt, keepbits, row_kept);
         } else {
-            if (d_cnt) col_stats_launch<T, double, true>(ctx, c, d_sum, d_sumsq, d_cnt);
-            else col_stats_launch<T, double, false>(ctx, c, d_sum, d_sumsq, d_cnt);
+            if (d_cnt) col_stats_launch<T, double, true>(ctx, c, d_sum, d_sumsq, d_cnt, keepbits, row_kept);
+            else col_stats_launch<T, double, false>(ctx, c, d_sum, d_sumsq, d_cnt, keepbits, row_kept);
         }
     }
     // row-sharded context: global column sums
@@ -180,8 +213,8 @@ void col_stats_device(salg_ctx* ctx, const salg_csr* c, double* d_sum, double* d
     if (d_sumsq) allreduce_f64(ctx, d_sumsq, (size_t)ncols);
     if (d_cnt) allreduce_f64(ctx, d_cnt, (size_t)ncols);
 }
-template void col_stats_device<float>(salg_ctx*, const salg_csr*, double*, double*, double*);
-template void col_stats_device<double>(salg_ctx*, const salg_csr*, double*, double*, double*);
+template void col_stats_device<float>(salg_ctx*, const salg_csr*, double*, double*, double*, const uint32_t*, int64_t*);
+template void col_stats_device<double>(salg_ctx*, const salg_csr*, double*, double*, double*, const uint32_t*, int64_t*);
 
 // ---- sum_row ----------------------------------------------------------------------------------------------
 template <typename T>
