@@ -3,23 +3,28 @@
 // Why: per stored entry a CUDA-core CSR kernel needs one distinct 256 B panel row from L1/L2;
 // measured on B200 that gather caps the products of the randomized-SVD power iteration at 2-6 % of the HBM
 // roofline (profiles/r01_v1_summary.md).  Here the operator is re-tiled once into 128-row x 64-column tiles
-// (entry stream sorted by tile, 8 B per entry); a CTA scatters one tile at a time into a zeroed dense bf16
-// tile in shared memory (UMMA canonical K-major layout, no swizzle) and contracts it with the matching
-// 64 x 64 slice of the panel by tcgen05.mma, accumulating the whole row block in TMEM.  The panel slice is
-// fetched ONCE per 128 rows x 64 columns instead of once per entry.
+// (entry stream sorted by tile, 8 B per entry).  A CTA scatters tiles into a zeroed dense fp16 tile in shared
+// memory (UMMA canonical K-major layout, no swizzle) and contracts it with the matching slice of the panel by
+// tcgen05.mma, accumulating in TMEM; the panel slice is fetched once per tile pair instead of once per entry.
 //
-// Precision: bf16 x bf16 products are exact in f32 and accumulate in f32.  The panel is split into three
-// bf16 terms (24 mantissa bits) and so is the operator unless every stored value is exactly representable
-// in bf16 (raw counts <= 256), in which case one term suffices.  Products kept: (a1,x1..x3) for exact
-// operators; (a1,x1..x3), (a2,x1..x2), (a3,x1) otherwise — relative error ~2^-22, f32-like.
+// Operand roles: the DENSE panel slice is the M = 128 operand (64 panel columns x 2 split terms, interleaved
+// m = 2*column + term), the SPARSE tile pair is the N operand (N = 256 rows for A X, N = 128 operator columns for
+// A^T Y).  A wide N keeps the shared-memory operand traffic per MMA below the 128 B/clk/SM the tensor core can
+// be fed with (an earlier layout with the panel as the N = 64 operand measured 80 clk per MMA instead of 32).
+//
+// Precision: fp16 x fp16 products are exact in f32 and accumulate in f32.  The panel is scaled by a power of two
+// (largest magnitude near 2^13) and split into two fp16 terms (22 significant bits); the operator likewise unless
+// every stored value is exactly representable in fp16 (raw counts <= 2048), in which case one term suffices.
+// The two term rows of a panel column are summed in the epilogue (adjacent TMEM lanes -> one shuffle).
 //
 // Roles inside a CTA (warp-specialised, all hand-offs through mbarriers):
-//   warps 0-7  scatter: un-scatter the previous tile's positions, scatter the new tile, fence.proxy.async
-//   warp  8    loader: cp.async.bulk of the pre-split panel slice (canonical layout) into a 2-3 stage ring
-//   warp  9    one thread issues tcgen05.mma (M=128, N=64, K=16 per instruction) and tcgen05.commit
-//   warps 10-13 epilogue: tcgen05.ld the f32 accumulator, apply the rank-1 centring term, store / atomically add
+//   warps 0-15   scatter: clear the tile buffer, scatter the unit's entries, fence.proxy.async, signal
+//   warp  16     panel-slice loader: cp.async.bulk of the pre-split slice (canonical layout) into a ring
+//   warp  17     one thread issues tcgen05.mma (M=128, K=16 per instruction) and tcgen05.commit
+//   warps 18-21  epilogue: tcgen05.ld the f32 accumulator, sum the term rows, rescale, store / atomically add
+//   warp  22     entry loader: lane j owns ring slot j, one cp.async.bulk per tile
 #include <cub/cub.cuh>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -29,19 +34,21 @@ constexpr int TC_RB = 128;          // tile rows
 constexpr int TC_CB = 64;           // tile columns
 constexpr int TC_SCATTER_WARPS = 16;
 constexpr int TC_SCATTER_THREADS = TC_SCATTER_WARPS * 32;
-constexpr int TC_THREADS = (TC_SCATTER_WARPS + 7) * 32;   // scatter warps + panel loader + mma + 4 epilogue + entry loader
+constexpr int TC_THREADS = (TC_SCATTER_WARPS + 10) * 32;   // + panel loader, mma, 4 epilogue, 4 entry loaders
 constexpr int TC_W_BLOAD = TC_SCATTER_WARPS, TC_W_MMA = TC_SCATTER_WARPS + 1, TC_W_EPI = TC_SCATTER_WARPS + 2,
               TC_W_ELOAD = TC_SCATTER_WARPS + 6;
-constexpr int TC_RMAX = 4;          // row blocks sharing one panel slice in the A X kernel
+constexpr int TC_RPAD = 4;            // row blocks are padded to a multiple of this (the A X kernel walks pairs)
 constexpr int TC_SLOT_ENTRIES = 768;  // entries per ring slot (one tile); denser tiles read their tail from global memory
 constexpr int TC_SLOT_BYTES = (TC_SLOT_ENTRIES + 2) * 8;
+constexpr int TC_S_BYTES = 32768;     // sparse operand buffer: 256 x 64 (A X) or 128 x 128 (A^T Y) fp16
 constexpr uint32_t TC_SPIN_LIMIT = 1u << 24;
 
 struct TcTiles {
     uint2* entries = nullptr;       // [nnz] .x = (local_row << 6) | local_col, .y = f32 bits of the value
     int64_t* tile_ptr = nullptr;    // [n_rb * n_cb + 1]
     int n_rb = 0, n_cb = 0;
-    int a_terms = 3;                // 1 when every value is exact in bf16
+    int a_terms = 2;                // 1 when every value is exact in fp16
+    float a_scale = 1.f;            // power of two applied to the operator values before the split
     int64_t nnz = 0;
 };
 
@@ -65,7 +72,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ unsigned long long g_tc_dbg[32];   // timing experiment counters of CTA 0
+__device__ unsigned long long g_tc_dbg[32];   // timing experiment counters of CTA 0 (SALG_TC_DBG=32)
 #define TC_T(acc) do { long long _t = clock64(); acc += _t - t_prev; t_prev = _t; } while (0)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t addr = smem_u32(bar), ok = 0, spins = 0;
@@ -80,28 +87,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (!ok && ++spins > TC_SPIN_LIMIT) __trap();   // never hang the GPU on a protocol bug
     } while (!ok);
 }
-// One lane polls, the warp follows: 32x fewer try_wait instructions competing for issue slots with the
-// single-thread MMA / loader roles.  `sleep_ns` > 0 backs the poll off for waits that are known to be long.
-__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane, unsigned sleep_ns = 0) {
-    if (lane == 0) {
-        if (sleep_ns) {
-            uint32_t addr = smem_u32(bar), ok = 0, spins = 0;
-            while (true) {
-                asm volatile(
-                    "{\n\t.reg .pred p;\n\t"
-                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                    "selp.u32 %0, 1, 0, p;\n\t}"
-                    : "=r"(ok)
-                    : "r"(addr), "r"(parity)
-                    : "memory");
-                if (ok) break;
-                if (++spins > TC_SPIN_LIMIT) __trap();
-                __nanosleep(sleep_ns);
-            }
-        } else {
-            mbar_wait(bar, parity);
-        }
-    }
+// one lane polls, the warp follows
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane) {
+    if (lane == 0) mbar_wait(bar, parity);
     __syncwarp();
 }
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -127,20 +115,10 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> f32, issued by ONE thread
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// KSTEPS consecutive K-steps of one (operator term, panel term) product in ONE asm block: the issuing thread is the
-// serial resource of the CTA, so per-MMA overhead is two 64-bit adds.  Descriptor start addresses advance by
-// `a_step` / `b_step` (16 B units) per K-step; only the first MMA may overwrite the accumulator.
-template <int KSTEPS>
-__device__ __forceinline__ void umma_bf16_run(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+// Four consecutive K-steps (K = 16 fp16 each) of one product in ONE asm block: the issuing thread is the serial
+// resource of the CTA, so per-MMA overhead is two 64-bit adds.  Descriptor start addresses advance by a_step /
+// b_step (16 B units) per K-step; only the first MMA may overwrite the accumulator.
+__device__ __forceinline__ void umma_f16_run4(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                               uint32_t accumulate_first, uint64_t a_step, uint64_t b_step) {
     asm volatile(
         "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
@@ -157,30 +135,14 @@ __device__ __forceinline__ void umma_bf16_run(uint32_t tmem_d, uint64_t desc_a, 
         "}"
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate_first), "l"(a_step), "l"(b_step)
         : "memory");
-    if (KSTEPS == 8) {
-        asm volatile(
-            "{\n\t.reg .pred q;\n\t.reg .b64 da, db;\n\t"
-            "setp.eq.b32 q, 0, 0;\n\t"
-            "mad.lo.u64 da, %4, 4, %1;\n\tmad.lo.u64 db, %5, 4, %2;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, q;\n\t"
-            "add.u64 da, da, %4;\n\tadd.u64 db, db, %5;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, q;\n\t"
-            "add.u64 da, da, %4;\n\tadd.u64 db, db, %5;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, q;\n\t"
-            "add.u64 da, da, %4;\n\tadd.u64 db, db, %5;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, q;\n\t"
-            "}"
-            ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "l"(a_step), "l"(b_step)
-            : "memory");
-    }
 }
 // shared-memory matrix descriptor, K-major, no swizzle: core matrix = 8 rows x 16 B (128 B contiguous);
 // LBO = byte distance between the two 16 B K-chunks of one instruction, SBO = distance between 8-row groups
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
 }
-// instruction descriptor: D f32, A/B bf16, both K-major, N = 64, M = 128
-constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+// instruction descriptor: D f32 (bit 4), A/B fp16 (format 0), both K-major, M = 128, N as given
+__host__ __device__ constexpr uint32_t tc_idesc(uint32_t n) { return (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24); }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -196,18 +158,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// bf16 term `t` (0,1,2) of a float: x ~ b0 + b1 + b2 with 8 significant bits each
-__device__ __forceinline__ unsigned short bf16_term(float x, int t) {
-    __nv_bfloat16 b = __float2bfloat16_rn(x);
-    if (t > 0) {
-        x -= __bfloat162float(b);
-        b = __float2bfloat16_rn(x);
-        if (t > 1) {
-            x -= __bfloat162float(b);
-            b = __float2bfloat16_rn(x);
-        }
-    }
-    return __bfloat16_as_ushort(b);
+// fp16 term `t` (0, 1) of a scaled float: x ~ h0 + h1 with 11 significant bits each
+__device__ __forceinline__ unsigned short f16_term(float x, int t) {
+    __half h = __float2half_rn(x);
+    if (t > 0) h = __float2half_rn(x - __half2float(h));
+    return __half_as_ushort(h);
 }
 
 // byte offset of element (mn, k) inside a canonical K-major no-swizzle operand whose 16 B K-chunks are
@@ -216,15 +171,24 @@ __device__ __forceinline__ uint32_t canon_off(uint32_t mn, uint32_t k, uint32_t 
     return (k >> 3) * chunk_stride + (mn >> 3) * 128u + (mn & 7u) * 16u + (k & 7u) * 2u;
 }
 
+// power-of-two scale that puts `amax` just below 2^14 (fp16 max is 65504; the second term is 2^-11 smaller)
+__host__ __device__ inline float tc_pow2_scale(float amax) {
+    if (!(amax > 0.f) || !isfinite(amax)) return 1.f;
+    int e;
+    frexpf(amax, &e);                 // amax = f * 2^e, f in [0.5, 1)
+    return ldexpf(1.f, 14 - e);
+}
+
 // ---- tile format builder -----------------------------------------------------------------------------------------
 template <typename T>
 __global__ void tc_keys_kernel(const int64_t* __restrict__ ptr, const uint32_t* __restrict__ col, const T* __restrict__ val,
                                int64_t nrows, int n_cb, uint32_t* __restrict__ keys, uint2* __restrict__ payload,
-                               int* __restrict__ inexact) {
+                               unsigned* __restrict__ info /* [0] inexact flag, [1] bits of max |v| */) {
     int lane = threadIdx.x & 31;
     int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
     bool bad = false;
+    float amax = 0.f;
     for (int64_t r = w; r < nrows; r += nw) {
         int64_t s = ptr[r], e = ptr[r + 1];
         uint32_t rb = (uint32_t)(r / TC_RB), lr = (uint32_t)(r % TC_RB);
@@ -233,18 +197,19 @@ __global__ void tc_keys_kernel(const int64_t* __restrict__ ptr, const uint32_t* 
             float v = (float)val[p];
             keys[p] = rb * (uint32_t)n_cb + c / TC_CB;
             payload[p] = make_uint2((lr << 6) | (c % TC_CB), __float_as_uint(v));
-            bad |= (__bfloat162float(__float2bfloat16_rn(v)) != v);
+            bad |= (__half2float(__float2half_rn(v)) != v);
+            amax = fmaxf(amax, fabsf(v));
         }
     }
-    if (bad) atomicOr(inexact, 1);
+    if (bad) atomicOr(&info[0], 1u);
+    atomicMax(&info[1], __float_as_uint(amax));
 }
 
 __global__ void tc_tile_ptr_kernel(const uint32_t* __restrict__ keys_sorted, int64_t nnz, int64_t n_tiles,
                                    int64_t* __restrict__ tile_ptr) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t > n_tiles) return;
-    // first position whose key >= t
-    int64_t lo = 0, hi = nnz;
+    int64_t lo = 0, hi = nnz;   // first position whose key >= t
     while (lo < hi) {
         int64_t mid = (lo + hi) >> 1;
         if ((int64_t)keys_sorted[mid] < t) lo = mid + 1; else hi = mid;
@@ -258,7 +223,7 @@ void* tc_build(salg_ctx* ctx, const salg_csr* c) {
     SALG_REQUIRE(c->nnz < ((int64_t)1 << 31), SALG_ERR_UNSUPPORTED, "tile format supports < 2^31 stored entries per GPU shard");
     TcTiles* t = new TcTiles();
     try {
-        t->n_rb = (int)(ceil_div(ceil_div(c->nrows, TC_RB), TC_RMAX) * TC_RMAX);   // padded: the A X kernel walks groups of TC_RMAX row blocks
+        t->n_rb = (int)(ceil_div(ceil_div(c->nrows, TC_RB), TC_RPAD) * TC_RPAD);
         t->n_cb = (int)ceil_div(c->ncols, TC_CB);
         t->nnz = c->nnz;
         int64_t n_tiles = (int64_t)t->n_rb * t->n_cb;
@@ -267,8 +232,8 @@ void* tc_build(salg_ctx* ctx, const salg_csr* c) {
         SALG_CUDA(cudaMalloc((void**)&t->entries, ((size_t)c->nnz + 1024) * sizeof(uint2)));
         SALG_CUDA(cudaMalloc((void**)&t->tile_ptr, (size_t)(n_tiles + 2) * 8));
         SALG_CUDA(cudaMemsetAsync(t->entries + c->nnz, 0, 1024 * sizeof(uint2), st));
-        DevBuf<int> flag(1, st);
-        SALG_CUDA(cudaMemsetAsync(flag.get(), 0, 4, st));
+        DevBuf<unsigned> info(2, st);
+        SALG_CUDA(cudaMemsetAsync(info.get(), 0, 8, st));
         int64_t nnz = c->nnz;
         DevBuf<uint32_t> keys((size_t)nnz + 1, st), keys_out((size_t)nnz + 1, st);
         if (nnz) {
@@ -276,7 +241,7 @@ void* tc_build(salg_ctx* ctx, const salg_csr* c) {
             int64_t want = ceil_div(c->nrows * 32, 256);
             int64_t cap = (int64_t)ctx->sm_count * 16;
             tc_keys_kernel<T><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(
-                c->row_ptr, c->col, (const T*)c->val, c->nrows, t->n_cb, keys.get(), payload.get(), flag.get());
+                c->row_ptr, c->col, (const T*)c->val, c->nrows, t->n_cb, keys.get(), payload.get(), info.get());
             ctx->n_launch++;
             SALG_CUDA(cudaGetLastError());
             int end_bit = 1;
@@ -293,10 +258,18 @@ void* tc_build(salg_ctx* ctx, const salg_csr* c) {
         tc_tile_ptr_kernel<<<(unsigned)ceil_div(n_tiles + 1, 256), 256, 0, st>>>(keys_out.get(), nnz, n_tiles, t->tile_ptr);
         ctx->n_launch++;
         SALG_CUDA(cudaGetLastError());
-        int h_flag = 0;
-        SALG_CUDA(cudaMemcpyAsync(&h_flag, flag.get(), 4, cudaMemcpyDeviceToHost, st));
+        unsigned h_info[2] = {0, 0};
+        SALG_CUDA(cudaMemcpyAsync(h_info, info.get(), 8, cudaMemcpyDeviceToHost, st));
         SALG_CUDA(cudaStreamSynchronize(st));
-        t->a_terms = h_flag ? 3 : 1;
+        float amax;
+        memcpy(&amax, &h_info[1], 4);
+        if (h_info[0]) {
+            t->a_terms = 2;
+            t->a_scale = tc_pow2_scale(amax);
+        } else {
+            t->a_terms = 1;
+            t->a_scale = 1.f;
+        }
     } catch (...) {
         cudaStreamSynchronize(st);
         tc_free(t);
@@ -306,226 +279,244 @@ void* tc_build(salg_ctx* ctx, const salg_csr* c) {
 }
 template void* tc_build<float>(salg_ctx*, const salg_csr*);
 
-// ---- panel pre-split into the canonical B-operand layout ---------------------------------------------------------
+// ---- panel pre-split into the canonical dense-operand layout -------------------------------------------------------
+__global__ void tc_absmax_kernel(const float* __restrict__ P, int64_t n_elems, unsigned* __restrict__ out_bits) {
+    float m = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_elems; i += (int64_t)gridDim.x * blockDim.x)
+        m = fmaxf(m, fabsf(P[i]));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));
+}
+// scales[0] = panel scale s, scales[1] = 1 / (s * a_scale)
+__global__ void tc_scale_kernel(const unsigned* __restrict__ amax_bits, float a_scale, float* __restrict__ scales) {
+    float s = tc_pow2_scale(__uint_as_float(*amax_bits));
+    scales[0] = s;
+    scales[1] = 1.f / (s * a_scale);
+}
 // Panel P (n x 64 f32, row-major; row index = K of the product).  Block b covers K rows [b*KB, (b+1)*KB);
-// out[b][term][canonical (N = 64 panel columns) x (K = KB)] bf16, 16 B K-chunks 1024 B apart.
+// out[b] = canonical (M = 128: m = 2*column + term) x (K = KB) fp16 operand, 16 B K-chunks 2048 B apart.
 template <int KB>
-__global__ void tc_prep_kernel(const float* __restrict__ P, int64_t n, int64_t n_blocks, unsigned short* __restrict__ out) {
+__global__ void tc_prep_kernel(const float* __restrict__ P, int64_t n, int64_t n_blocks, const float* __restrict__ scales,
+                               unsigned short* __restrict__ out) {
     // one thread per (k, 4 panel columns)
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t total = n_blocks * KB * 16;
     if (i >= total) return;
+    const float s = scales[0];
     int nq = (int)(i & 15);
     int64_t k = i >> 4;
     int64_t b = k / KB;
     uint32_t kl = (uint32_t)(k % KB);
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (k < n) v = *reinterpret_cast<const float4*>(P + k * LP + nq * 4);
-    float x[4] = {v.x, v.y, v.z, v.w};
-    unsigned short* base = out + (size_t)b * 3 * (KB * 64);
+    float x[4] = {v.x * s, v.y * s, v.z * s, v.w * s};
+    unsigned short* base = out + (size_t)b * (128 * KB);
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        uint32_t off = canon_off((uint32_t)(nq * 4 + j), kl, 1024u) >> 1;
+        uint32_t pc = (uint32_t)(nq * 4 + j);
 #pragma unroll
-        for (int t = 0; t < 3; t++) base[(size_t)t * (KB * 64) + off] = bf16_term(x[j], t);
+        for (int t = 0; t < 2; t++) base[canon_off(2 * pc + t, kl, 2048u) >> 1] = f16_term(x[j], t);
     }
 }
 
 // ---- work sequences ---------------------------------------------------------------------------------------------------
-// Every role of a CTA walks the same private sequence of tiles q = 0 .. q_total-1 (ring slot q % NS holds the
-// tile's entries) grouped into units (one scatter + MMA pass each).
-//   A X   : groups of R row blocks gb = blockIdx.x, +gridDim.x, ...; order (group, cb, r); unit = one tile
-//   A^T Y : row blocks [rb0, rb1), tiles cb_lo .. cb_hi-1 of each; unit = two adjacent tiles (one when odd)
+// Every role of a CTA walks the same private sequence of units s = 0 .. n_units-1; a unit (one scatter + MMA pass
+// per operator term) is a pair of tiles whose entry lists sit in ring slot s % NS.
+//   A X   : row-block pairs g = blockIdx.x, +gridDim.x, ...; order (pair, cb); tiles (2g, cb) and (2g+1, cb)
+//   A^T Y : row blocks [rb0, rb1), units u of each: tiles cb_lo + 2u and cb_lo + 2u + 1 (one tile when odd)
 struct TcSeq {
     int n_cb;
     bool aty;
-    int R, n_groups_mine;          // A X
-    int rb0, rb1, cb_lo, ntr;      // A^T Y
-    __device__ __forceinline__ int64_t q_total() const {
-        return aty ? (int64_t)(rb1 - rb0) * ntr : (int64_t)n_groups_mine * n_cb * R;
-    }
-    __device__ __forceinline__ int64_t tile_id(int64_t q) const {
-        if (!aty) {
-            int64_t per = (int64_t)n_cb * R;
-            int64_t i = q / per;
-            int rem = (int)(q - i * per);
-            int cb = rem / R, r = rem - cb * R;
-            int64_t rb = ((int64_t)blockIdx.x + i * gridDim.x) * R + r;
-            return rb * n_cb + cb;
-        }
-        int64_t rbi = q / ntr;
-        int c = (int)(q - rbi * ntr);
-        return (rb0 + rbi) * n_cb + cb_lo + c;
-    }
+    int n_pairs_mine;                  // A X
+    int rb0, rb1, cb_lo, ntr, upr;     // A^T Y (upr = units per row block)
     __device__ __forceinline__ int64_t n_units() const {
-        return aty ? (int64_t)(rb1 - rb0) * ((ntr + 1) / 2) : q_total();
+        return aty ? (int64_t)(rb1 - rb0) * upr : (int64_t)n_pairs_mine * n_cb;
     }
-    // unit s -> first tile index and tile count
-    __device__ __forceinline__ void unit(int64_t s, int64_t& q0, int& nt) const {
-        if (!aty) { q0 = s; nt = 1; return; }
-        int upr = (ntr + 1) / 2;
-        int64_t rbi = s / upr;
-        int u = (int)(s - rbi * upr);
-        q0 = rbi * ntr + 2 * u;
-        nt = (2 * u + 1 < ntr) ? 2 : 1;
+    // tile ids of unit s (t1 < 0: the unit has a single tile)
+    __device__ __forceinline__ void tiles(int64_t s, int64_t& t0, int64_t& t1) const {
+        if (!aty) {
+            int64_t i = s / n_cb;
+            int cb = (int)(s - i * n_cb);
+            int64_t g = (int64_t)blockIdx.x + i * gridDim.x;
+            t0 = (2 * g) * n_cb + cb;
+            t1 = (2 * g + 1) * n_cb + cb;
+        } else {
+            int64_t rbi = s / upr;
+            int u = (int)(s - rbi * upr);
+            t0 = (rb0 + rbi) * n_cb + cb_lo + 2 * u;
+            t1 = (2 * u + 1 < ntr) ? t0 + 1 : -1;
+        }
     }
 };
 
-struct TcSlotMeta { long long e0; int n; int pad; };   // first entry (global index), entry count, leading pad (0/1)
+struct TcSlotMeta { long long e0[2]; int n[2]; int pad[2]; };   // per tile: first entry, entry count, leading pad (0/1)
+constexpr int TC_LOADER_WARPS = 4;   // entry loaders: warp w serves units s = w (mod 4), one lane each (a suspended
+                                     // try_wait parks the whole warp, so lanes of one warp cannot wait independently)
 
-// ---- entry loader role: one warp streams the tiles' entry lists into the shared-memory ring ----------------------------
-// Lane j owns ring slot j: the NS tiles of a batch are handled in parallel (pointer fetch, slot wait, one
-// cp.async.bulk per lane), so the per-tile cost of this single warp is a few cycles and up to NS tiles
-// (~NS * 4.6 KB) are in flight per SM without holding registers.  Pointers are fetched one batch ahead.
+// ---- entry loader role ---------------------------------------------------------------------------------------------------
 template <int NS>
 __device__ __forceinline__ void tc_entry_loader(const uint2* __restrict__ entries, const int64_t* __restrict__ tile_ptr,
                                                 const TcSeq& seq, uint8_t* sRing, TcSlotMeta* sMeta, uint64_t* e_full,
-                                                uint64_t* e_free, int lane, int dbg) {
-    const int64_t qt = seq.q_total();
-    if (lane >= NS) return;
-    long long e0 = 0, e1 = 0;
-    if (lane < qt) {
-        int64_t t = seq.tile_id(lane);
-        e0 = tile_ptr[t];
-        e1 = tile_ptr[t + 1];
-    }
-    uint32_t use = 0;
-    for (int64_t qb = 0; qb < qt; qb += NS, use++) {
-        const int64_t q = qb + lane;
-        long long ne0 = 0, ne1 = 0;
-        if (q + NS < qt) {
-            int64_t t = seq.tile_id(q + NS);
-            ne0 = tile_ptr[t];
-            ne1 = tile_ptr[t + 1];
-        }
-        if (q < qt) {
-            if (use > 0) mbar_wait(&e_free[lane], (use - 1) & 1);
-            const int n = (int)(e1 - e0);
+                                                uint64_t* e_free, int w) {
+    static_assert(NS % TC_LOADER_WARPS == 0, "a loader warp must always meet the same slots");
+    const int64_t nu = seq.n_units();
+    long long p[4] = {0, 0, 0, 0};       // tile pointers of the current unit: [e0, e1) of tile 0, [e0, e1) of tile 1
+    bool two = false;
+    auto fetch = [&](int64_t s, long long (&o)[4], bool& o_two) {
+        int64_t t0, t1;
+        seq.tiles(s, t0, t1);
+        o[0] = tile_ptr[t0];
+        o[1] = tile_ptr[t0 + 1];
+        o_two = t1 >= 0;
+        o[2] = o_two ? tile_ptr[t1] : 0;
+        o[3] = o_two ? tile_ptr[t1 + 1] : 0;
+    };
+    if (w < nu) fetch(w, p, two);
+    for (int64_t s = w; s < nu; s += TC_LOADER_WARPS) {
+        long long np[4] = {0, 0, 0, 0};
+        bool ntwo = false;
+        if (s + TC_LOADER_WARPS < nu) fetch(s + TC_LOADER_WARPS, np, ntwo);   // next unit's pointers, overlapped
+        const int slot = (int)(s % NS);
+        const uint32_t use = (uint32_t)(s / NS);
+        if (use > 0) mbar_wait(&e_free[slot], (use - 1) & 1);
+        uint32_t bytes[2] = {0, 0};
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const long long e0 = p[2 * k], e1 = p[2 * k + 1];
+            const int n = (k == 0 || two) ? (int)(e1 - e0) : 0;
             const int pad = (int)(e0 & 1);
-            int cnt = n + pad;
+            int cnt = n > 0 ? n + pad : 0;
             if (cnt > TC_SLOT_ENTRIES) cnt = TC_SLOT_ENTRIES;
             cnt = (cnt + 1) & ~1;
-            sMeta[lane].e0 = e0;
-            sMeta[lane].n = n;
-            sMeta[lane].pad = pad;
-            if (cnt > 0 && !(dbg & 128)) {
-                mbar_expect_tx(&e_full[lane], (uint32_t)cnt * 8u);
-                bulk_g2s(sRing + (size_t)lane * TC_SLOT_BYTES, entries + (e0 - pad), (uint32_t)cnt * 8u, &e_full[lane]);
-            } else {
-                mbar_arrive(&e_full[lane]);
-            }
+            sMeta[slot].e0[k] = e0;
+            sMeta[slot].n[k] = n;
+            sMeta[slot].pad[k] = pad;
+            bytes[k] = (uint32_t)cnt * 8u;
         }
-        e0 = ne0;
-        e1 = ne1;
+        if (bytes[0] + bytes[1] > 0) {
+            mbar_expect_tx(&e_full[slot], bytes[0] + bytes[1]);
+            uint8_t* dst = sRing + (size_t)slot * (2 * TC_SLOT_BYTES);
+            if (bytes[0]) bulk_g2s(dst, entries + (p[0] - (p[0] & 1)), bytes[0], &e_full[slot]);
+            if (bytes[1]) bulk_g2s(dst + TC_SLOT_BYTES, entries + (p[2] - (p[2] & 1)), bytes[1], &e_full[slot]);
+        } else {
+            mbar_arrive(&e_full[slot]);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) p[k] = np[k];
+        two = ntwo;
     }
 }
 
 // ---- scatter role -----------------------------------------------------------------------------------------------------------
-// Per pass: wait until the MMA that read this A buffer has retired, clear the buffer with 128-bit stores (cheaper in
-// instructions than undoing the previous scatter), barrier among the scatter warps, scatter the unit's entries as
-// bf16 term `term`, make the writes visible to the tensor core (async proxy) and signal the MMA thread.
-template <bool ATY, int A_BYTES, int NS>
-__device__ __forceinline__ void tc_scatter_role(const uint2* __restrict__ entries, const TcSeq& seq, int a_terms, uint8_t* sA,
-                                                const uint8_t* sRing, const TcSlotMeta* sMeta, uint64_t* e_full, uint64_t* e_free,
-                                                uint64_t* a_full, uint64_t* a_free, int tid, int dbg) {
-    const int64_t nu = seq.n_units();
+// Per pass: wait until the MMA that read this buffer has retired, clear it with 128-bit stores, barrier among the
+// scatter warps, scatter the unit's entries as fp16 term `term`, make the writes visible to the tensor core
+// (async proxy) and signal the MMA thread (one arrival per warp).  A thread owns at most two entries of each tile
+// (denser tiles take the slow loop); all of them are loaded before any is processed so the shared-memory latencies
+// overlap.
+// Operand coordinates: A X   n = 128*k + local_row (k = tile of the pair), K = local column, chunk stride 4096
+//                      A^T Y n =  64*k + local_col,                         K = local row,    chunk stride 2048
+template <bool ATY>
+__device__ __forceinline__ void tc_scatter_one(uint8_t* S, uint2 en, int k, float a_scale, int term) {
+    uint32_t lr = en.x >> 6, lc = en.x & 63u;
+    uint32_t off = ATY ? canon_off(lc + 64u * k, lr, 2048u) : canon_off(lr + 128u * k, lc, 4096u);
+    *reinterpret_cast<unsigned short*>(S + off) = f16_term(__uint_as_float(en.y) * a_scale, term);
+}
+
+template <bool ATY, int NS>
+__device__ __forceinline__ void tc_scatter_role(const uint2* __restrict__ entries, int64_t n_units, int a_terms, float a_scale,
+                                                uint8_t* sS, const uint8_t* sRing, const TcSlotMeta* sMeta, uint64_t* e_full,
+                                                uint64_t* e_free, uint64_t* s_full, uint64_t* s_free, int tid) {
     const int lane = tid & 31;
     uint32_t pass = 0;
-    long long c_unit = 0, c_afree = 0, c_zero = 0, c_efull = 0, c_scat = 0, c_arr = 0, c_efree = 0, t_prev = clock64(), t_begin = t_prev;
-    for (int64_t s = 0; s < nu; s++) {
-        int64_t q0;
-        int nt;
-        seq.unit(s, q0, nt);
-        TC_T(c_unit);
+    for (int64_t s = 0; s < n_units; s++) {
+        const int slot = (int)(s % NS);
         for (int term = 0; term < a_terms; term++) {
-            const int ab = pass & 1;
+            const int sb = pass & 1;
             const uint32_t use = pass >> 1;
-            if (use > 0) mbar_wait_warp(&a_free[ab], (use - 1) & 1, lane);
-            TC_T(c_afree);
-            uint8_t* A = sA + ab * A_BYTES;
-            if (!(dbg & 512)) {
+            if (use > 0) mbar_wait_warp(&s_free[sb], (use - 1) & 1, lane);
+            uint8_t* S = sS + sb * TC_S_BYTES;
 #pragma unroll
-                for (int i = 0; i < A_BYTES / 16 / TC_SCATTER_THREADS; i++)
-                    reinterpret_cast<uint4*>(A)[i * TC_SCATTER_THREADS + tid] = make_uint4(0, 0, 0, 0);
-                named_bar_sync(1, TC_SCATTER_THREADS);
-            }
-            TC_T(c_zero);
+            for (int i = 0; i < TC_S_BYTES / 16 / TC_SCATTER_THREADS; i++)
+                reinterpret_cast<uint4*>(S)[i * TC_SCATTER_THREADS + tid] = make_uint4(0, 0, 0, 0);
+            if (term == 0) mbar_wait_warp(&e_full[slot], (uint32_t)(s / NS) & 1, lane);
+            // gather this thread's entries of both tiles first (independent shared-memory loads)
+            const int n0 = sMeta[slot].n[0], n1 = sMeta[slot].n[1];
+            const uint2* sl0 = reinterpret_cast<const uint2*>(sRing + (size_t)slot * (2 * TC_SLOT_BYTES)) + sMeta[slot].pad[0];
+            const uint2* sl1 = reinterpret_cast<const uint2*>(sRing + (size_t)slot * (2 * TC_SLOT_BYTES) + TC_SLOT_BYTES) +
+                               sMeta[slot].pad[1];
+            const int lim = TC_SLOT_ENTRIES - 1;     // entries guaranteed to sit in the slot whatever the pad
+            uint2 en[4];
+            bool ok[4];
+            ok[0] = tid < n0 && tid < lim;
+            ok[1] = tid + TC_SCATTER_THREADS < n0 && tid + TC_SCATTER_THREADS < lim;
+            ok[2] = tid < n1 && tid < lim;
+            ok[3] = tid + TC_SCATTER_THREADS < n1 && tid + TC_SCATTER_THREADS < lim;
+            en[0] = ok[0] ? sl0[tid] : make_uint2(0, 0);
+            en[1] = ok[1] ? sl0[tid + TC_SCATTER_THREADS] : make_uint2(0, 0);
+            en[2] = ok[2] ? sl1[tid] : make_uint2(0, 0);
+            en[3] = ok[3] ? sl1[tid + TC_SCATTER_THREADS] : make_uint2(0, 0);
+            named_bar_sync(1, TC_SCATTER_THREADS);       // every thread's clearing stores precede every scatter store
 #pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (ok[j]) tc_scatter_one<ATY>(S, en[j], j >> 1, a_scale, term);
+            // rare: tiles with more entries than two per thread / than the slot holds
             for (int k = 0; k < 2; k++) {
-                if (k < nt) {
-                    const int64_t q = q0 + k;
-                    const int slot = (int)(q % NS);
-                    if (term == 0) mbar_wait_warp(&e_full[slot], (uint32_t)(q / NS) & 1, lane);
-                    TC_T(c_efull);
-                    const int n = (dbg & 1) ? 0 : sMeta[slot].n;
-                    const int pad = sMeta[slot].pad;
-                    const uint2* sl = reinterpret_cast<const uint2*>(sRing + (size_t)slot * TC_SLOT_BYTES) + pad;
-                    const int in_slot = TC_SLOT_ENTRIES - pad;
-                    for (int i = tid; i < n; i += TC_SCATTER_THREADS) {
-                        uint2 en = (i < in_slot) ? sl[i] : entries[sMeta[slot].e0 + i];
-                        uint32_t lr = en.x >> 6, lc = en.x & 63u;
-                        uint32_t off = ATY ? canon_off(lc + (k ? 64u : 0u), lr, 2048u) : canon_off(lr, lc, 2048u);
-                        *reinterpret_cast<unsigned short*>(A + off) = bf16_term(__uint_as_float(en.y), term);
-                    }
-                    TC_T(c_scat);
+                const int n = k ? n1 : n0;
+                const uint2* sl = k ? sl1 : sl0;
+                const long long e0 = sMeta[slot].e0[k];
+                for (int i = tid; i < n; i += TC_SCATTER_THREADS) {
+                    if (i < lim && i < 2 * TC_SCATTER_THREADS) continue;      // handled above
+                    uint2 e = (i < lim) ? sl[i] : entries[e0 + i];
+                    tc_scatter_one<ATY>(S, e, k, a_scale, term);
                 }
             }
-            if (!(dbg & 8)) fence_proxy_async();
+            fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&a_full[ab]);
-            TC_T(c_arr);
+            if (lane == 0) {
+                mbar_arrive(&s_full[sb]);
+                if (term == a_terms - 1) mbar_arrive(&e_free[slot]);   // every lane of this warp has read the slot
+            }
             pass++;
         }
-        // the unit's ring slots can be refilled once every lane of this warp has read them
-        __syncwarp();
-        if (lane == 0) {
-            mbar_arrive(&e_free[(int)(q0 % NS)]);
-            if (nt > 1) mbar_arrive(&e_free[(int)((q0 + 1) % NS)]);
-        }
-        TC_T(c_efree);
-    }
-    if ((dbg & 32) && blockIdx.x == 0 && tid == 0) {
-        g_tc_dbg[0] = clock64() - t_begin; g_tc_dbg[1] = c_unit; g_tc_dbg[2] = c_afree; g_tc_dbg[3] = c_zero; g_tc_dbg[4] = c_efull;
-        g_tc_dbg[5] = c_scat; g_tc_dbg[6] = c_arr; g_tc_dbg[7] = c_efree; g_tc_dbg[8] = pass;
     }
 }
 
 // ---- Y = A X - 1 corr^T -----------------------------------------------------------------------------------------------------
 struct AxSmem {
-    static constexpr int A_BYTES = TC_RB * TC_CB * 2;        // 16 KB per buffer (one bf16 term)
-    static constexpr int B_BYTES = 3 * TC_CB * 64 * 2;       // 24 KB per stage (three terms)
+    static constexpr int D_BYTES = 128 * TC_CB * 2;          // 16 KB per stage: panel slice (M = 128) x (K = 64)
     static constexpr int NB = 3;
-    static constexpr int NS = 16;
-    static constexpr int TOTAL = 2 * A_BYTES + NB * B_BYTES + NS * TC_SLOT_BYTES + 1024;
+    static constexpr int NS = 8;                             // ring slots (one unit = two tiles each)
+    static constexpr int TOTAL = 2 * TC_S_BYTES + NB * D_BYTES + NS * 2 * TC_SLOT_BYTES + 1024;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
-tc_ax_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ tile_ptr, int n_rb, int n_cb, int a_terms, int R,
-             int64_t nrows, const uint8_t* __restrict__ Xprep, float* __restrict__ Y, const double* __restrict__ corr, int dbg) {
+tc_ax_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ tile_ptr, int n_rb, int n_cb, int a_terms,
+             float a_scale, int64_t nrows, const uint8_t* __restrict__ Xprep, const float* __restrict__ scales,
+             float* __restrict__ Y, const double* __restrict__ corr) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t* sA = smem;
-    uint8_t* sB = sA + 2 * AxSmem::A_BYTES;
-    uint8_t* sRing = sB + AxSmem::NB * AxSmem::B_BYTES;
-    __shared__ uint64_t a_full[2], a_free[2], b_full[AxSmem::NB], b_free[AxSmem::NB], acc_full[2], acc_free[2];
+    uint8_t* sS = smem;
+    uint8_t* sD = sS + 2 * TC_S_BYTES;
+    uint8_t* sRing = sD + AxSmem::NB * AxSmem::D_BYTES;
+    __shared__ uint64_t s_full[2], s_free[2], d_full[AxSmem::NB], d_free[AxSmem::NB], acc_full[2], acc_free[2];
     __shared__ uint64_t e_full[AxSmem::NS], e_free[AxSmem::NS];
     __shared__ TcSlotMeta sMeta[AxSmem::NS];
     __shared__ uint32_t s_tmem;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n_groups = n_rb / R;
-    const int n_mine = ((int)blockIdx.x < n_groups) ? (n_groups - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    const uint32_t tmem_cols = 2u * (uint32_t)R * 64u;
+    const int n_pairs = n_rb / 2;
+    const int n_mine = ((int)blockIdx.x < n_pairs) ? (n_pairs - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     if (tid == 0) {
         for (int i = 0; i < 2; i++) {
-            mbar_init(&a_full[i], TC_SCATTER_WARPS);   // one arrival per scatter warp: per-thread arrivals serialise on the barrier word
-            mbar_init(&a_free[i], 1);
+            mbar_init(&s_full[i], TC_SCATTER_WARPS);
+            mbar_init(&s_free[i], 1);
             mbar_init(&acc_full[i], 1);
             mbar_init(&acc_free[i], 4);
         }
         for (int i = 0; i < AxSmem::NB; i++) {
-            mbar_init(&b_full[i], 1);
-            mbar_init(&b_free[i], 1);
+            mbar_init(&d_full[i], 1);
+            mbar_init(&d_free[i], 1);
         }
         for (int i = 0; i < AxSmem::NS; i++) {
             mbar_init(&e_full[i], 1);
@@ -533,19 +524,18 @@ tc_ax_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ tile
         }
         fence_barrier_init();
     }
-    if (warp == 0) tmem_alloc(&s_tmem, tmem_cols);
-    for (int i = tid; i < 2 * AxSmem::A_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0, 0, 0, 0);
+    if (warp == 0) tmem_alloc(&s_tmem, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = s_tmem;
-    TcSeq seq{n_cb, false, R, n_mine, 0, 0, 0, 0};
+    TcSeq seq{n_cb, false, n_mine, 0, 0, 0, 0, 0};
 
     if (warp < TC_SCATTER_WARPS) {
-        tc_scatter_role<false, AxSmem::A_BYTES, AxSmem::NS>(entries, seq, a_terms, sA, sRing, sMeta, e_full, e_free, a_full,
-                                                            a_free, tid, dbg);
-    } else if (warp == TC_W_ELOAD) {
-        tc_entry_loader<AxSmem::NS>(entries, tile_ptr, seq, sRing, sMeta, e_full, e_free, lane, dbg);
+        tc_scatter_role<false, AxSmem::NS>(entries, seq.n_units(), a_terms, a_scale, sS, sRing, sMeta, e_full, e_free, s_full,
+                                           s_free, tid);
+    } else if (warp >= TC_W_ELOAD) {
+        if (lane == 0) tc_entry_loader<AxSmem::NS>(entries, tile_ptr, seq, sRing, sMeta, e_full, e_free, warp - TC_W_ELOAD);
     } else if (warp == TC_W_BLOAD) {
         // ================= panel-slice loader =================
         if (lane == 0) {
@@ -554,10 +544,9 @@ tc_ax_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ tile
                 for (int cb = 0; cb < n_cb; cb++, it++) {
                     const int bb = it % AxSmem::NB;
                     const uint32_t use = it / AxSmem::NB;
-                    if (use > 0) mbar_wait(&b_free[bb], (use - 1) & 1);
-                    if (dbg & 4) { mbar_arrive(&b_full[bb]); continue; }
-                    mbar_expect_tx(&b_full[bb], AxSmem::B_BYTES);
-                    bulk_g2s(sB + bb * AxSmem::B_BYTES, Xprep + (size_t)cb * AxSmem::B_BYTES, AxSmem::B_BYTES, &b_full[bb]);
+                    if (use > 0) mbar_wait(&d_free[bb], (use - 1) & 1);
+                    mbar_expect_tx(&d_full[bb], AxSmem::D_BYTES);
+                    bulk_g2s(sD + bb * AxSmem::D_BYTES, Xprep + (size_t)cb * AxSmem::D_BYTES, AxSmem::D_BYTES, &d_full[bb]);
                 }
             }
         }
@@ -565,105 +554,98 @@ tc_ax_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ tile
         // ================= MMA issuer =================
         if (lane == 0) {
             uint32_t pass = 0, it = 0;
-            long long c_acc = 0, c_b = 0, c_a = 0, c_issue = 0, c_commit = 0, t_prev = clock64(), t_begin = t_prev;
-            uint64_t a_desc[2], b_desc[AxSmem::NB];
-            for (int i = 0; i < 2; i++) a_desc[i] = umma_desc(smem_u32(sA + i * AxSmem::A_BYTES), 2048, 128);
-            for (int i = 0; i < AxSmem::NB; i++) b_desc[i] = umma_desc(smem_u32(sB + i * AxSmem::B_BYTES), 1024, 128);
+            uint64_t s_desc[2], d_desc[AxSmem::NB];
+            for (int i = 0; i < 2; i++) s_desc[i] = umma_desc(smem_u32(sS + i * TC_S_BYTES), 4096, 128);
+            for (int i = 0; i < AxSmem::NB; i++) d_desc[i] = umma_desc(smem_u32(sD + i * AxSmem::D_BYTES), 2048, 128);
+            constexpr uint32_t idesc = tc_idesc(256);
+            long long c_acc = 0, c_d = 0, c_s = 0, c_issue = 0, c_commit = 0, t_prev = clock64(), t_begin = t_prev;
             for (int gi = 0; gi < n_mine; gi++) {
                 const int as = gi & 1;
                 if (gi >= 2) mbar_wait(&acc_free[as], ((gi >> 1) - 1) & 1);
                 tc_fence_after();
                 TC_T(c_acc);
+                const uint32_t d_tmem = tmem_base + (uint32_t)as * 256u;
                 for (int cb = 0; cb < n_cb; cb++, it++) {
                     const int bb = it % AxSmem::NB;
-                    mbar_wait(&b_full[bb], (it / AxSmem::NB) & 1);
-                    TC_T(c_b);
-                    const uint64_t db0 = b_desc[bb];
-                    for (int r = 0; r < R; r++) {
-                        const uint32_t d_tmem = tmem_base + (uint32_t)(as * R + r) * 64u;
-                        for (int term = 0; term < a_terms; term++) {
-                            const int ab = pass & 1;
-                            mbar_wait(&a_full[ab], (pass >> 1) & 1);
-                            tc_fence_after();
-                            TC_T(c_a);
-                            const int nx = (a_terms == 1) ? 3 : 3 - term;
-                            if (!(dbg & 2)) {
-                                const uint64_t da0 = a_desc[ab];
-                                umma_bf16_run<4>(d_tmem, da0, db0, TC_IDESC, (cb | term) != 0, 256, 128);
-                                if (nx > 1) umma_bf16_run<4>(d_tmem, da0, db0 + 512, TC_IDESC, 1, 256, 128);
-                                if (nx > 2) umma_bf16_run<4>(d_tmem, da0, db0 + 1024, TC_IDESC, 1, 256, 128);
-                            }
-                            TC_T(c_issue);
-                            if (dbg & 16) mbar_arrive(&a_free[ab]); else umma_commit(&a_free[ab]);
-                            TC_T(c_commit);
-                            pass++;
-                        }
+                    mbar_wait(&d_full[bb], (it / AxSmem::NB) & 1);
+                    TC_T(c_d);
+                    for (int term = 0; term < a_terms; term++) {
+                        const int sb = pass & 1;
+                        mbar_wait(&s_full[sb], (pass >> 1) & 1);
+                        tc_fence_after();
+                        TC_T(c_s);
+                        // K = 64: four K-steps; dense operand advances 2 chunks x 2048 B, sparse operand 2 x 4096 B
+                        umma_f16_run4(d_tmem, d_desc[bb], s_desc[sb], idesc, (cb | term) != 0, 256, 512);
+                        TC_T(c_issue);
+                        umma_commit(&s_free[sb]);
+                        TC_T(c_commit);
+                        pass++;
                     }
-                    if (dbg & 16) mbar_arrive(&b_free[bb]); else umma_commit(&b_free[bb]);
+                    umma_commit(&d_free[bb]);
                 }
                 umma_commit(&acc_full[as]);
             }
-            if ((dbg & 32) && blockIdx.x == 0) {
-                g_tc_dbg[10] = clock64() - t_begin; g_tc_dbg[11] = c_acc; g_tc_dbg[12] = c_b; g_tc_dbg[13] = c_a; g_tc_dbg[14] = c_issue; g_tc_dbg[15] = c_commit;
+            if (blockIdx.x == 0) {
+                g_tc_dbg[10] = clock64() - t_begin; g_tc_dbg[11] = c_acc; g_tc_dbg[12] = c_d; g_tc_dbg[13] = c_s; g_tc_dbg[14] = c_issue; g_tc_dbg[15] = c_commit;
             }
         }
     } else if (warp >= TC_W_EPI && warp < TC_W_EPI + 4) {
         // ================= epilogue warps =================
-        const int q = warp & 3;
+        // TMEM lane m = 2*column + term: the two term rows of a panel column sit in adjacent lanes of one warp
+        const int qd = warp & 3;
+        const int pc = qd * 16 + (lane >> 1);
+        const float inv = scales[1];
+        const float cr = corr ? (float)corr[pc] : 0.f;
+        long long c_wait = 0, c_work = 0, t_prev = clock64();
         for (int gi = 0; gi < n_mine; gi++) {
             const int as = gi & 1;
-            mbar_wait_warp(&acc_full[as], (gi >> 1) & 1, lane, 256);
+            mbar_wait_warp(&acc_full[as], (gi >> 1) & 1, lane);
             tc_fence_after();
-            const int64_t g = (int64_t)blockIdx.x + (int64_t)gi * gridDim.x;
-            for (int r = 0; r < ((dbg & 256) ? 0 : R); r++) {
-                const int64_t row = (g * R + r) * TC_RB + q * 32 + lane;
+            TC_T(c_wait);
+            const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)gi * gridDim.x) * 256;
+#pragma unroll 1
+            for (int c = 0; c < 8; c++) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)as * 256u + c * 32, v);
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * R + r) * 64u + h * 32, v);
-                    if (row < nrows) {
-                        float4* o = reinterpret_cast<float4*>(Y + row * LP + h * 32);
-#pragma unroll
-                        for (int j = 0; j < 8; j++) {
-                            float4 rr;
-                            rr.x = __uint_as_float(v[4 * j + 0]) - (corr ? (float)corr[h * 32 + 4 * j + 0] : 0.f);
-                            rr.y = __uint_as_float(v[4 * j + 1]) - (corr ? (float)corr[h * 32 + 4 * j + 1] : 0.f);
-                            rr.z = __uint_as_float(v[4 * j + 2]) - (corr ? (float)corr[h * 32 + 4 * j + 2] : 0.f);
-                            rr.w = __uint_as_float(v[4 * j + 3]) - (corr ? (float)corr[h * 32 + 4 * j + 3] : 0.f);
-                            o[j] = rr;
-                        }
-                    }
+                for (int j = 0; j < 32; j++) {
+                    float x = __uint_as_float(v[j]);
+                    x += __shfl_xor_sync(0xFFFFFFFFu, x, 1);
+                    const int64_t row = row0 + c * 32 + j;
+                    if (!(lane & 1) && row < nrows) Y[row * LP + pc] = x * inv - cr;
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_free[as]);
+            TC_T(c_work);
         }
+        if (blockIdx.x == 0 && warp == TC_W_EPI && lane == 0) { g_tc_dbg[16] = c_wait; g_tc_dbg[17] = c_work; }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
 // ---- Z += A^T Y (Z pre-initialised with the centring term) ------------------------------------------------------------------
 struct AtySmem {
-    static constexpr int A_BYTES = 128 * TC_RB * 2;          // 32 KB: M = 128 operator columns x K = 128 rows
-    static constexpr int B_BYTES = 3 * 64 * TC_RB * 2;       // 48 KB: three terms of the Y row block
+    static constexpr int D_BYTES = 128 * TC_RB * 2;          // 32 KB per stage: Y row block (M = 128) x (K = 128 rows)
     static constexpr int NB = 2;
-    static constexpr int NS = 10;
-    static constexpr int TOTAL = 2 * A_BYTES + NB * B_BYTES + NS * TC_SLOT_BYTES + 1024;
+    static constexpr int NS = 8;                             // ring slots (one unit = two tiles each)
+    static constexpr int G = 8;                               // operator column blocks per CTA: 4 units x 128 TMEM columns
+    static constexpr int TOTAL = 2 * TC_S_BYTES + NB * D_BYTES + NS * 2 * TC_SLOT_BYTES + 1024;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_aty_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ tile_ptr, int n_rb, int n_cb, int a_terms,
-              int64_t n_eff, const uint8_t* __restrict__ Yprep, float* __restrict__ Z, int G, int n_groups, int rb_per_range,
-              uint32_t tmem_cols, int dbg) {
+              float a_scale, int64_t n_eff, const uint8_t* __restrict__ Yprep, const float* __restrict__ scales,
+              float* __restrict__ Z, int n_groups, int rb_per_range) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t* sA = smem;
-    uint8_t* sB = sA + 2 * AtySmem::A_BYTES;
-    uint8_t* sRing = sB + AtySmem::NB * AtySmem::B_BYTES;
-    __shared__ uint64_t a_full[2], a_free[2], b_full[AtySmem::NB], b_free[AtySmem::NB], acc_full;
+    uint8_t* sS = smem;
+    uint8_t* sD = sS + 2 * TC_S_BYTES;
+    uint8_t* sRing = sD + AtySmem::NB * AtySmem::D_BYTES;
+    __shared__ uint64_t s_full[2], s_free[2], d_full[AtySmem::NB], d_free[AtySmem::NB], acc_full;
     __shared__ uint64_t e_full[AtySmem::NS], e_free[AtySmem::NS];
     __shared__ TcSlotMeta sMeta[AtySmem::NS];
     __shared__ uint32_t s_tmem;
@@ -672,19 +654,19 @@ tc_aty_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ til
     const int g = blockIdx.x % n_groups, range = blockIdx.x / n_groups;
     const int rb0 = range * rb_per_range;
     const int rb1 = (rb0 + rb_per_range < n_rb) ? rb0 + rb_per_range : n_rb;
-    const int cb_lo = g * G;
-    const int cb_hi = (cb_lo + G < n_cb) ? cb_lo + G : n_cb;     // exclusive
+    const int cb_lo = g * AtySmem::G;
+    const int cb_hi = (cb_lo + AtySmem::G < n_cb) ? cb_lo + AtySmem::G : n_cb;     // exclusive
     const int ntr = cb_hi - cb_lo;
     const int n_units = (ntr + 1) / 2;
 
     if (tid == 0) {
         for (int i = 0; i < 2; i++) {
-            mbar_init(&a_full[i], TC_SCATTER_WARPS);   // one arrival per scatter warp: per-thread arrivals serialise on the barrier word
-            mbar_init(&a_free[i], 1);
+            mbar_init(&s_full[i], TC_SCATTER_WARPS);
+            mbar_init(&s_free[i], 1);
         }
         for (int i = 0; i < AtySmem::NB; i++) {
-            mbar_init(&b_full[i], 1);
-            mbar_init(&b_free[i], 1);
+            mbar_init(&d_full[i], 1);
+            mbar_init(&d_free[i], 1);
         }
         for (int i = 0; i < AtySmem::NS; i++) {
             mbar_init(&e_full[i], 1);
@@ -693,79 +675,77 @@ tc_aty_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ til
         mbar_init(&acc_full, 1);
         fence_barrier_init();
     }
-    if (warp == 0) tmem_alloc(&s_tmem, tmem_cols);
-    for (int i = tid; i < 2 * AtySmem::A_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0, 0, 0, 0);
+    if (warp == 0) tmem_alloc(&s_tmem, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = s_tmem;
     const bool active = rb0 < rb1 && ntr > 0;
-    TcSeq seq{n_cb, true, 0, 0, rb0, rb1, cb_lo, ntr};
+    TcSeq seq{n_cb, true, 0, rb0, rb1, cb_lo, ntr, n_units};
 
     if (warp < TC_SCATTER_WARPS) {
         if (active)
-            tc_scatter_role<true, AtySmem::A_BYTES, AtySmem::NS>(entries, seq, a_terms, sA, sRing, sMeta, e_full, e_free, a_full,
-                                                                 a_free, tid, dbg);
-    } else if (warp == TC_W_ELOAD) {
-        if (active) tc_entry_loader<AtySmem::NS>(entries, tile_ptr, seq, sRing, sMeta, e_full, e_free, lane, dbg);
+            tc_scatter_role<true, AtySmem::NS>(entries, seq.n_units(), a_terms, a_scale, sS, sRing, sMeta, e_full, e_free, s_full,
+                                               s_free, tid);
+    } else if (warp >= TC_W_ELOAD) {
+        if (active && lane == 0)
+            tc_entry_loader<AtySmem::NS>(entries, tile_ptr, seq, sRing, sMeta, e_full, e_free, warp - TC_W_ELOAD);
     } else if (warp == TC_W_BLOAD) {
         if (lane == 0 && active) {
             uint32_t it = 0;
             for (int rb = rb0; rb < rb1; rb++, it++) {
                 const int bb = it % AtySmem::NB;
                 const uint32_t use = it / AtySmem::NB;
-                if (use > 0) mbar_wait(&b_free[bb], (use - 1) & 1);
-                if (dbg & 4) { mbar_arrive(&b_full[bb]); continue; }
-                mbar_expect_tx(&b_full[bb], AtySmem::B_BYTES);
-                bulk_g2s(sB + bb * AtySmem::B_BYTES, Yprep + (size_t)rb * AtySmem::B_BYTES, AtySmem::B_BYTES, &b_full[bb]);
+                if (use > 0) mbar_wait(&d_free[bb], (use - 1) & 1);
+                mbar_expect_tx(&d_full[bb], AtySmem::D_BYTES);
+                bulk_g2s(sD + bb * AtySmem::D_BYTES, Yprep + (size_t)rb * AtySmem::D_BYTES, AtySmem::D_BYTES, &d_full[bb]);
             }
         }
     } else if (warp == TC_W_MMA) {
         if (lane == 0 && active) {
             uint32_t pass = 0, it = 0;
-            uint64_t a_desc[2], b_desc[AtySmem::NB];
-            for (int i = 0; i < 2; i++) a_desc[i] = umma_desc(smem_u32(sA + i * AtySmem::A_BYTES), 2048, 128);
-            for (int i = 0; i < AtySmem::NB; i++) b_desc[i] = umma_desc(smem_u32(sB + i * AtySmem::B_BYTES), 1024, 128);
+            uint64_t s_desc[2], d_desc[AtySmem::NB];
+            for (int i = 0; i < 2; i++) s_desc[i] = umma_desc(smem_u32(sS + i * TC_S_BYTES), 2048, 128);
+            for (int i = 0; i < AtySmem::NB; i++) d_desc[i] = umma_desc(smem_u32(sD + i * AtySmem::D_BYTES), 2048, 128);
+            constexpr uint32_t idesc = tc_idesc(128);
             for (int rb = rb0; rb < rb1; rb++, it++) {
                 const int bb = it % AtySmem::NB;
-                mbar_wait(&b_full[bb], (it / AtySmem::NB) & 1);
-                const uint64_t db0 = b_desc[bb];
+                mbar_wait(&d_full[bb], (it / AtySmem::NB) & 1);
                 for (int u = 0; u < n_units; u++) {
-                    const uint32_t d_tmem = tmem_base + u * 64;
+                    const uint32_t d_tmem = tmem_base + (uint32_t)u * 128u;
                     for (int term = 0; term < a_terms; term++) {
-                        const int ab = pass & 1;
-                        mbar_wait(&a_full[ab], (pass >> 1) & 1);
+                        const int sb = pass & 1;
+                        mbar_wait(&s_full[sb], (pass >> 1) & 1);
                         tc_fence_after();
-                        const int nx = (a_terms == 1) ? 3 : 3 - term;
-                        if (!(dbg & 2)) {
-                            const uint64_t da0 = a_desc[ab];
-                            umma_bf16_run<8>(d_tmem, da0, db0, TC_IDESC, ((rb - rb0) | term) != 0, 256, 128);
-                            if (nx > 1) umma_bf16_run<8>(d_tmem, da0, db0 + 1024, TC_IDESC, 1, 256, 128);
-                            if (nx > 2) umma_bf16_run<8>(d_tmem, da0, db0 + 2048, TC_IDESC, 1, 256, 128);
-                        }
-                        if (dbg & 16) mbar_arrive(&a_free[ab]); else umma_commit(&a_free[ab]);
+                        // K = 128 rows: eight K-steps, both operands advance 2 chunks x 2048 B per step
+                        umma_f16_run4(d_tmem, d_desc[bb], s_desc[sb], idesc, ((rb - rb0) | term) != 0, 256, 256);
+                        umma_f16_run4(d_tmem, d_desc[bb] + 1024, s_desc[sb] + 1024, idesc, 1, 256, 256);
+                        umma_commit(&s_free[sb]);
                         pass++;
                     }
                 }
-                if (dbg & 16) mbar_arrive(&b_free[bb]); else umma_commit(&b_free[bb]);
+                umma_commit(&d_free[bb]);
             }
             umma_commit(&acc_full);
         }
     } else if (warp >= TC_W_EPI && warp < TC_W_EPI + 4) {
         if (active) {
-            const int q = warp & 3;
-            mbar_wait_warp(&acc_full, 0, lane, 1024);
+            const int qd = warp & 3;
+            const int pc = qd * 16 + (lane >> 1);
+            const float inv = scales[1];
+            mbar_wait_warp(&acc_full, 0, lane);
             tc_fence_after();
             for (int u = 0; u < n_units; u++) {
-                const int64_t cA = (int64_t)(cb_lo + 2 * u) * TC_CB + q * 32 + lane;   // operator column of this TMEM lane
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
+#pragma unroll 1
+                for (int c = 0; c < 4; c++) {
                     uint32_t v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + u * 64 + h * 32, v);
-                    if (cA < n_eff && !(dbg & 2)) {
-                        float* o = Z + cA * LP + h * 32;
+                    tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)u * 128u + c * 32, v);
 #pragma unroll
-                        for (int j = 0; j < 32; j++) atomicAdd(o + j, __uint_as_float(v[j]));
+                    for (int j = 0; j < 32; j++) {
+                        float x = __uint_as_float(v[j]);
+                        x += __shfl_xor_sync(0xFFFFFFFFu, x, 1);
+                        const int64_t cA = (int64_t)(cb_lo + 2 * u) * TC_CB + c * 32 + j;   // operator column
+                        if (!(lane & 1) && cA < n_eff) atomicAdd(Z + cA * LP + pc, x * inv);
                     }
                 }
             }
@@ -774,7 +754,7 @@ tc_aty_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ til
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
 // Z[r][j] = -mu[r] * cs[j]  (or 0)
@@ -786,24 +766,42 @@ __global__ void tc_init_z_kernel(float* __restrict__ Z, int64_t n_eff, const flo
 
 bool tc_enabled(const salg_ctx* ctx) { return ctx->spmm_impl == 0; }
 
-static int tc_dbg() {
-    const char* e = getenv("SALG_TC_DBG");   // timing experiments only: 1 skip scatter, 2 skip MMA, 4 skip panel loads, 8 skip proxy fence
-    return e ? atoi(e) : 0;
-}
-
-static void tc_dbg_print(salg_ctx* ctx, const char* what) {
-    if (!(tc_dbg() & 32)) return;
-    unsigned long long h[32];
-    cudaStreamSynchronize(ctx->stream);
-    cudaMemcpyFromSymbol(h, g_tc_dbg, sizeof(h));
-    fprintf(stderr, "[tc %s] scatter total %llu passes %llu: unit %llu a_free %llu zero+bar %llu e_full %llu scatter %llu fence+arrive %llu e_free %llu\n",
-            what, h[0], h[8], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
-    fprintf(stderr, "[tc %s] mma total %llu: acc_free %llu b_full %llu a_full %llu issue %llu commit %llu\n", what, h[10], h[11], h[12], h[13], h[14], h[15]);
-}
-
 static TcTiles* tiles_of(salg_ctx* ctx, const salg_csr* c) {
     if (!c->tc) c->tc = tc_build<float>(ctx, c);
     return (TcTiles*)c->tc;
+}
+
+// scale + split the panel into the canonical dense operand (device-side scale: no host round trip)
+template <int KB>
+static void tc_prepare_panel(salg_ctx* ctx, const float* P, int64_t n, int64_t n_blocks, float a_scale, float* d_scales,
+                             unsigned* d_amax, uint8_t* out) {
+    cudaStream_t st = ctx->stream;
+    SALG_CUDA(cudaMemsetAsync(d_amax, 0, 4, st));
+    if (n > 0) {
+        int64_t ne = n * LP;
+        int64_t want = ceil_div(ne, 256 * 8);
+        int64_t cap = (int64_t)ctx->sm_count * 8;
+        tc_absmax_kernel<<<(unsigned)(want < cap ? (want > 0 ? want : 1) : cap), 256, 0, st>>>(P, ne, d_amax);
+        ctx->n_launch++;
+    }
+    tc_scale_kernel<<<1, 1, 0, st>>>(d_amax, a_scale, d_scales);
+    ctx->n_launch++;
+    int64_t total = n_blocks * KB * 16;
+    tc_prep_kernel<KB><<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(P, n, n_blocks, d_scales, (unsigned short*)out);
+    ctx->n_launch++;
+    SALG_CUDA(cudaGetLastError());
+}
+
+static void tc_dbg_print(salg_ctx* ctx, const char* what) {
+    const char* e = getenv("SALG_TC_DBG");
+    if (!e || !(atoi(e) & 32)) return;
+    unsigned long long h[32];
+    cudaStreamSynchronize(ctx->stream);
+    cudaMemcpyFromSymbol(h, g_tc_dbg, sizeof(h));
+    fprintf(stderr, "[tc %s] scatter total %llu passes %llu: s_free %llu zero %llu bar %llu e_full %llu scatter %llu fence %llu arrive %llu e_free %llu\n",
+            what, h[0], h[9], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8]);
+    fprintf(stderr, "[tc %s] mma total %llu: acc_free %llu d_full %llu s_full %llu issue %llu commit %llu | epilogue wait %llu work %llu\n", what,
+            h[10], h[11], h[12], h[13], h[14], h[15], h[16], h[17]);
 }
 
 // Y (nrows x 64) = A X - 1 corr^T
@@ -813,22 +811,15 @@ void tc_spmm_A(salg_ctx* ctx, const salg_csr* c, const float* X, float* Y, const
     if (c->nrows == 0) return;
     double bytes = (double)c->nnz * 8 + (double)(c->nrows + 1) * 8 + (double)c->ncols * 60 * 4 + (double)c->nrows * 60 * 4;
     ProfScope ps(ctx, PROF_SPMM, bytes);   // includes the panel pre-split
-    DevBuf<uint8_t> Xprep((size_t)t->n_cb * AxSmem::B_BYTES, st);
-    {
-        int64_t total = (int64_t)t->n_cb * TC_CB * 16;
-        tc_prep_kernel<TC_CB><<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(X, c->ncols, t->n_cb, (unsigned short*)Xprep.get());
-        ctx->n_launch++;
-        SALG_CUDA(cudaGetLastError());
-    }
+    DevBuf<uint8_t> Xprep((size_t)t->n_cb * AxSmem::D_BYTES, st);
+    DevBuf<float> scales(2, st);
+    DevBuf<unsigned> amax(1, st);
+    tc_prepare_panel<TC_CB>(ctx, X, c->ncols, t->n_cb, t->a_scale, scales.get(), amax.get(), Xprep.get());
     SALG_CUDA(cudaFuncSetAttribute(tc_ax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AxSmem::TOTAL));
-    // R row blocks share one panel slice (cuts the L2 -> shared-memory panel traffic by R) as long as every SM
-    // still gets several groups
-    int R = TC_RMAX;
-    while (R > 1 && t->n_rb / R < 4 * ctx->sm_count) R >>= 1;
-    int n_groups = t->n_rb / R;
-    int grid = n_groups < ctx->sm_count ? n_groups : ctx->sm_count;
-    tc_ax_kernel<<<grid, TC_THREADS, AxSmem::TOTAL, st>>>(t->entries, t->tile_ptr, t->n_rb, t->n_cb, t->a_terms, R, c->nrows,
-                                                          Xprep.get(), Y, corr, tc_dbg());
+    int n_pairs = t->n_rb / 2;
+    int grid = n_pairs < ctx->sm_count ? n_pairs : ctx->sm_count;
+    tc_ax_kernel<<<grid, TC_THREADS, AxSmem::TOTAL, st>>>(t->entries, t->tile_ptr, t->n_rb, t->n_cb, t->a_terms, t->a_scale,
+                                                          c->nrows, Xprep.get(), scales.get(), Y, corr);
     ctx->n_launch++;
     SALG_CUDA(cudaGetLastError());
     tc_dbg_print(ctx, "ax");
@@ -845,28 +836,21 @@ void tc_spmm_At(salg_ctx* ctx, const salg_csr* c, const float* Y, float* Z, cons
     ctx->n_launch++;
     SALG_CUDA(cudaGetLastError());
     if (c->nrows == 0) return;
-    DevBuf<uint8_t> Yprep((size_t)t->n_rb * AtySmem::B_BYTES, st);
-    {
-        int64_t total = (int64_t)t->n_rb * TC_RB * 16;
-        tc_prep_kernel<TC_RB><<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(Y, c->nrows, t->n_rb, (unsigned short*)Yprep.get());
-        ctx->n_launch++;
-        SALG_CUDA(cudaGetLastError());
-    }
-    int G = t->n_cb < 16 ? t->n_cb : 16;
-    int n_groups = (int)ceil_div(t->n_cb, G);
+    DevBuf<uint8_t> Yprep((size_t)t->n_rb * AtySmem::D_BYTES, st);
+    DevBuf<float> scales(2, st);
+    DevBuf<unsigned> amax(1, st);
+    tc_prepare_panel<TC_RB>(ctx, Y, c->nrows, t->n_rb, t->a_scale, scales.get(), amax.get(), Yprep.get());
+    int n_groups = (int)ceil_div(t->n_cb, AtySmem::G);
     int n_rb_real = (int)ceil_div(c->nrows, TC_RB);
     int ranges = ctx->sm_count / n_groups;
     if (ranges < 1) ranges = 1;
     if (ranges > n_rb_real) ranges = n_rb_real;
     int rb_per_range = (int)ceil_div(n_rb_real, ranges);
     ranges = (int)ceil_div(n_rb_real, rb_per_range);
-    int n_units = (G + 1) / 2;
-    uint32_t tmem_cols = 32;
-    while (tmem_cols < (uint32_t)n_units * 64) tmem_cols <<= 1;
     SALG_CUDA(cudaFuncSetAttribute(tc_aty_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AtySmem::TOTAL));
     tc_aty_kernel<<<n_groups * ranges, TC_THREADS, AtySmem::TOTAL, st>>>(t->entries, t->tile_ptr, n_rb_real, t->n_cb, t->a_terms,
-                                                                         c->ncols, Yprep.get(), Z, G, n_groups, rb_per_range,
-                                                                         tmem_cols, tc_dbg());
+                                                                         t->a_scale, c->ncols, Yprep.get(), scales.get(), Z,
+                                                                         n_groups, rb_per_range);
     ctx->n_launch++;
     SALG_CUDA(cudaGetLastError());
 }
