@@ -236,7 +236,11 @@ def run_ours(args, wl):
     sampler.start()
     ctx.timer_start()
     for _ in range(args.steps):
+        _t0 = time.perf_counter()
         step_resident()
+        if os.environ.get("SALG_BENCH_VERBOSE") and rank == 0:
+            ctx.sync()
+            print(f"[resident] step {1e3 * (time.perf_counter() - _t0):.1f} ms", file=sys.stderr, flush=True)
     ms = ctx.timer_stop()
     barrier()
     clocks = sampler.finish()

@@ -1,9 +1,19 @@
 // api.cu — context lifecycle, error reporting, profiling records, NCCL plumbing.
+#include <mutex>
+#include <set>
+
 #include "common.cuh"
 
 namespace salg {
 
 static thread_local std::string g_last_error;
+static std::mutex g_ctx_mutex;
+static std::set<const salg_ctx*> g_live_ctx;
+
+bool ctx_alive(const salg_ctx* ctx) {
+    std::lock_guard<std::mutex> lk(g_ctx_mutex);
+    return ctx && g_live_ctx.count(ctx) != 0;
+}
 
 void set_last_error(const std::string& msg) { g_last_error = msg; }
 
@@ -96,6 +106,10 @@ static salg_ctx* ctx_new(int device) {
         uint64_t thr = UINT64_MAX;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
+    {
+        std::lock_guard<std::mutex> lk(g_ctx_mutex);
+        g_live_ctx.insert(c);
+    }
     return c;
 }
 
@@ -164,6 +178,10 @@ int salg_ctx_create_dist(int device, int rank, int nranks, const void* uid, salg
 int salg_ctx_destroy(salg_ctx* c) {
     return guarded([&] {
         if (!c) return;
+        {
+            std::lock_guard<std::mutex> lk(g_ctx_mutex);
+            g_live_ctx.erase(c);
+        }
         cudaSetDevice(c->device);
         cudaStreamSynchronize(c->stream);
         prof_collect(c);

@@ -207,6 +207,22 @@ template <> struct dtype_of<double> { static constexpr int value = SALG_F64; };
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// ---- device memory: stream-ordered pool (release threshold = max, see ctx_new) ---------------------------------
+// cudaMalloc / cudaFree synchronise the device and were measured to stall a fit by 10-600 ms on multi-GB buffers;
+// every buffer of the library therefore comes from the context's stream-ordered pool.  `owner` may already be
+// destroyed when a handle is freed late (interpreter shutdown): then fall back to the synchronous call.
+bool ctx_alive(const salg_ctx* ctx);
+inline void* dev_alloc(salg_ctx* ctx, size_t bytes) {
+    void* p = nullptr;
+    SALG_CUDA(cudaMallocAsync(&p, bytes ? bytes : 1, ctx->stream));
+    return p;
+}
+inline void dev_free(salg_ctx* owner, void* p) {
+    if (!p) return;
+    if (ctx_alive(owner)) cudaFreeAsync(p, owner->stream);
+    else cudaFree(p);
+}
+
 // ---- csr.cu ---------------------------------------------------------------------------------------
 salg_csr* csr_alloc(salg_ctx* ctx, int dtype, int64_t nrows, int64_t ncols, int64_t nnz);
 void csr_destroy(salg_csr* c);
@@ -243,7 +259,7 @@ template <typename T> void spmm_At(salg_ctx* ctx, const salg_csr* c, const T* Y,
 // ---- tc.cu ----------------------------------------------------------------------------------------
 // tile-densified tcgen05 products (f32 operators only).  SALG_SPMM_IMPL=chunk selects the CUDA-core kernels.
 bool tc_enabled(const salg_ctx* ctx);
-void tc_free(void* tiles);
+void tc_free(salg_ctx* owner, void* tiles);
 void tc_spmm_A(salg_ctx* ctx, const salg_csr* c, const float* X, float* Y, const double* corr);
 void tc_spmm_At(salg_ctx* ctx, const salg_csr* c, const float* Y, float* Z, const float* mu, const double* corr);
 

@@ -18,10 +18,10 @@ salg_csr* csr_alloc(salg_ctx* ctx, int dtype, int64_t nrows, int64_t ncols, int6
     c->ncols = ncols;
     c->nnz = nnz;
     try {
-        SALG_CUDA(cudaMalloc((void**)&c->row_ptr, (size_t)(nrows + 1) * sizeof(int64_t)));
+        c->row_ptr = (int64_t*)dev_alloc(ctx, (size_t)(nrows + 1) * sizeof(int64_t));
         // +16 entries of slack so vectorised tail loads never leave the allocation
-        SALG_CUDA(cudaMalloc((void**)&c->col, ((size_t)nnz + 16) * sizeof(uint32_t)));
-        SALG_CUDA(cudaMalloc((void**)&c->val, ((size_t)nnz + 16) * dsize(dtype)));
+        c->col = (uint32_t*)dev_alloc(ctx, ((size_t)nnz + 16) * sizeof(uint32_t));
+        c->val = dev_alloc(ctx, ((size_t)nnz + 16) * dsize(dtype));
     } catch (...) {
         csr_destroy(c);
         throw;
@@ -30,11 +30,11 @@ salg_csr* csr_alloc(salg_ctx* ctx, int dtype, int64_t nrows, int64_t ncols, int6
 }
 
 void csr_invalidate_transpose(const salg_csr* c) {
-    if (c->t_ptr) cudaFree(c->t_ptr);
-    if (c->t_idx) cudaFree(c->t_idx);
-    if (c->t_val) cudaFree(c->t_val);
-    if (c->t_chunk_row) cudaFree(c->t_chunk_row);
-    if (c->tc) tc_free(c->tc);
+    dev_free(c->ctx, c->t_ptr);
+    dev_free(c->ctx, c->t_idx);
+    dev_free(c->ctx, c->t_val);
+    dev_free(c->ctx, c->t_chunk_row);
+    if (c->tc) tc_free(c->ctx, c->tc);
     c->tc = nullptr;
     c->t_chunk_row = nullptr;
     c->t_ptr = nullptr;
@@ -45,15 +45,12 @@ void csr_invalidate_transpose(const salg_csr* c) {
 
 void csr_destroy(salg_csr* c) {
     if (!c) return;
-    if (c->ctx) {
-        cudaSetDevice(c->ctx->device);
-        cudaStreamSynchronize(c->ctx->stream);
-    }
+    if (ctx_alive(c->ctx)) cudaSetDevice(c->ctx->device);
     csr_invalidate_transpose(c);
-    if (c->row_ptr) cudaFree(c->row_ptr);
-    if (c->col) cudaFree(c->col);
-    if (c->val) cudaFree(c->val);
-    if (c->chunk_row) cudaFree(c->chunk_row);
+    dev_free(c->ctx, c->row_ptr);
+    dev_free(c->ctx, c->col);
+    dev_free(c->ctx, c->val);
+    dev_free(c->ctx, c->chunk_row);
     delete c;
 }
 
@@ -303,8 +300,7 @@ salg_csr* csr_select_columns(salg_ctx* ctx, const salg_csr* c, const uint8_t* ma
         SALG_CUDA(cudaGetLastError());
     }
     DevBuf<int64_t> d_cnt((size_t)nrows + 1, st);
-    int64_t* new_ptr = nullptr;
-    SALG_CUDA(cudaMalloc((void**)&new_ptr, (size_t)(nrows + 1) * 8));
+    int64_t* new_ptr = (int64_t*)dev_alloc(ctx, (size_t)(nrows + 1) * 8);
     salg_csr* out = nullptr;
     try {
         double bytes = (double)c->nnz * (sizeof(T) + 4) + 2.0 * (double)(nrows + 1) * 8;
@@ -327,8 +323,8 @@ salg_csr* csr_select_columns(salg_ctx* ctx, const salg_csr* c, const uint8_t* ma
         out->nnz = nnz_eff;
         out->row_ptr = new_ptr;
         new_ptr = nullptr;
-        SALG_CUDA(cudaMalloc((void**)&out->col, ((size_t)nnz_eff + 16) * 4));
-        SALG_CUDA(cudaMalloc((void**)&out->val, ((size_t)nnz_eff + 16) * sizeof(T)));
+        out->col = (uint32_t*)dev_alloc(ctx, ((size_t)nnz_eff + 16) * 4);
+        out->val = dev_alloc(ctx, ((size_t)nnz_eff + 16) * sizeof(T));
         SALG_CUDA(cudaMemsetAsync(out->col + nnz_eff, 0, 16 * 4, st));
         SALG_CUDA(cudaMemsetAsync((T*)out->val + nnz_eff, 0, 16 * sizeof(T), st));
         if (nrows && c->nnz) {
@@ -338,7 +334,7 @@ salg_csr* csr_select_columns(salg_ctx* ctx, const salg_csr* c, const uint8_t* ma
             SALG_CUDA(cudaGetLastError());
         }
     } catch (...) {
-        if (new_ptr) cudaFree(new_ptr);
+        dev_free(ctx, new_ptr);
         if (out) csr_destroy(out);
         throw;
     }
@@ -390,9 +386,9 @@ void csr_ensure_transpose(salg_ctx* ctx, const salg_csr* c) {
     SALG_REQUIRE(c->nrows < ((int64_t)1 << 32), SALG_ERR_UNSUPPORTED, "row count must fit 32 bits");
     int64_t nnz = c->nnz, ncols = c->ncols;
     ProfScope ps(ctx, PROF_TRANSPOSE, (double)nnz * 2.0 * (sizeof(T) + 4));
-    SALG_CUDA(cudaMalloc((void**)&c->t_ptr, (size_t)(ncols + 1) * 8));
-    SALG_CUDA(cudaMalloc((void**)&c->t_idx, ((size_t)nnz + 16) * 4));
-    SALG_CUDA(cudaMalloc((void**)&c->t_val, ((size_t)nnz + 16) * sizeof(T)));
+    c->t_ptr = (int64_t*)dev_alloc(ctx, (size_t)(ncols + 1) * 8);
+    c->t_idx = (uint32_t*)dev_alloc(ctx, ((size_t)nnz + 16) * 4);
+    c->t_val = dev_alloc(ctx, ((size_t)nnz + 16) * sizeof(T));
     SALG_CUDA(cudaMemsetAsync(c->t_idx + nnz, 0, 16 * 4, st));
     SALG_CUDA(cudaMemsetAsync((T*)c->t_val + nnz, 0, 16 * sizeof(T), st));
     // column histogram -> t_ptr

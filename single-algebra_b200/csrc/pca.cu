@@ -63,19 +63,16 @@ __global__ void panel_sub_kernel(T* __restrict__ a, const T* __restrict__ b, int
 template <typename T>
 static void pca_release(salg_pca* p) {
     if (!p) return;
-    if (p->d_V) cudaFree(p->d_V);
-    if (p->d_mean) cudaFree(p->d_mean);
-    if (p->d_scores) cudaFree(p->d_scores);
-    if (p->d_tscores) cudaFree(p->d_tscores);
+    dev_free(p->ctx, p->d_V);
+    dev_free(p->ctx, p->d_mean);
+    dev_free(p->ctx, p->d_scores);
+    dev_free(p->ctx, p->d_tscores);
     delete p;
 }
 
 static void pca_destroy(salg_pca* p) {
     if (!p) return;
-    if (p->ctx) {
-        cudaSetDevice(p->ctx->device);
-        cudaStreamSynchronize(p->ctx->stream);
-    }
+    if (ctx_alive(p->ctx)) cudaSetDevice(p->ctx->device);
     pca_release<float>(p);
 }
 
@@ -160,7 +157,7 @@ static salg_pca* pca_fit(salg_ctx* ctx, const salg_csr* x, const salg_pca_params
             d_kept.alloc((size_t)n_eff, st);
             SALG_CUDA(cudaMemcpyAsync(d_kept.get(), kept.data(), (size_t)n_eff * 4, cudaMemcpyHostToDevice, st));
         }
-        SALG_CUDA(cudaMalloc(&P->d_mean, (size_t)n_eff * sizeof(T)));
+        P->d_mean = dev_alloc(ctx, (size_t)n_eff * sizeof(T));
         T* d_mu = (T*)P->d_mean;
         gather_mean_kernel<T><<<(unsigned)ceil_div(n_eff, 256), 256, 0, st>>>(d_sum.get(), mask ? d_kept.get() : nullptr,
                                                                               n_eff, 1.0 / n_d, center ? 1 : 0, d_mu);
@@ -169,7 +166,7 @@ static salg_pca* pca_fit(salg_ctx* ctx, const salg_csr* x, const salg_pca_params
         SALG_CUDA(cudaStreamSynchronize(st));   // kept / h_* staging no longer needed by the device
 
         const int rank = (int)std::min<int64_t>(prm->n_components, std::min<int64_t>(n_total, n_eff));
-        SALG_CUDA(cudaMalloc(&P->d_V, (size_t)n_eff * LP * sizeof(T)));
+        P->d_V = dev_alloc(ctx, (size_t)n_eff * LP * sizeof(T));
         T* d_V = (T*)P->d_V;
         DevBuf<int> d_flag(1, st);
         SALG_CUDA(cudaMemsetAsync(d_flag.get(), 0, 4, st));
@@ -252,7 +249,7 @@ static salg_pca* pca_fit(salg_ctx* ctx, const salg_csr* x, const salg_pca_params
             // fit_transform = fit, then transform of the same rows (pca/sparse/mod.rs:355-358):
             // (X - 1 mu^T) V on the kept columns, computed while the compacted operator is still resident.
             // (U S from the factorisation is only the projection of this onto range(Q).)
-            SALG_CUDA(cudaMalloc(&P->d_scores, (size_t)std::max<int64_t>(op->nrows, 1) * LP * sizeof(T)));
+            P->d_scores = dev_alloc(ctx, (size_t)std::max<int64_t>(op->nrows, 1) * LP * sizeof(T));
             DevBuf<double> corr(LP, st);
             if (center) panel_colsum<T>(ctx, d_V, n_eff, d_mu, corr.get());
             spmm_A<T>(ctx, op, d_V, (T*)P->d_scores, center ? corr.get() : nullptr, false);
@@ -601,9 +598,9 @@ int salg_pca_transform_device(salg_ctx* ctx, const salg_pca* cp, const salg_csr*
         size_t es = p->dtype == SALG_F64 ? 8 : 4;
         if (p->tscores_rows < x->nrows || !p->d_tscores) {
             SALG_CUDA(cudaStreamSynchronize(ctx->stream));
-            if (p->d_tscores) cudaFree(p->d_tscores);
+            dev_free(p->ctx, p->d_tscores);
             p->d_tscores = nullptr;
-            SALG_CUDA(cudaMalloc(&p->d_tscores, (size_t)std::max<int64_t>(x->nrows, 1) * LP * es));
+            p->d_tscores = dev_alloc(ctx, (size_t)std::max<int64_t>(x->nrows, 1) * LP * es);
             p->tscores_rows = x->nrows;
         }
         if (x->nrows == 0) return;

@@ -36,8 +36,7 @@ __global__ void chunk_row_kernel(const int64_t* __restrict__ ptr, int64_t nr, in
 
 uint32_t* build_chunk_rows(salg_ctx* ctx, const int64_t* ptr, int64_t nr, int64_t nnz) {
     int64_t n_chunks = ceil_div(nnz, SPMM_CHUNK);
-    uint32_t* out = nullptr;
-    SALG_CUDA(cudaMalloc((void**)&out, (size_t)(n_chunks + 1) * 4));
+    uint32_t* out = (uint32_t*)dev_alloc(ctx, (size_t)(n_chunks + 1) * 4);
     if (n_chunks) {
         chunk_row_kernel<<<(unsigned)ceil_div(n_chunks, 256), 256, 0, ctx->stream>>>(ptr, nr, n_chunks, SPMM_CHUNK, out);
         ctx->n_launch++;

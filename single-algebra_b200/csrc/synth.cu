@@ -125,8 +125,7 @@ extern "C" int salg_csr_synth(salg_ctx* ctx, int dtype, uint64_t seed, int64_t r
         synth_count_kernel<<<grid, 256, 0, st>>>(a, cnt.get());
         ctx->n_launch++;
         SALG_CUDA(cudaGetLastError());
-        int64_t* ptr = nullptr;
-        SALG_CUDA(cudaMalloc((void**)&ptr, (size_t)(nrows + 1) * 8));
+        int64_t* ptr = (int64_t*)dev_alloc(ctx, (size_t)(nrows + 1) * 8);
         salg_csr* c = nullptr;
         try {
             exclusive_scan_i64(ctx, cnt.get(), ptr, nrows + 1);
@@ -142,8 +141,8 @@ extern "C" int salg_csr_synth(salg_ctx* ctx, int dtype, uint64_t seed, int64_t r
             c->row_ptr = ptr;
             ptr = nullptr;
             size_t es = dtype == SALG_F64 ? 8 : 4;
-            SALG_CUDA(cudaMalloc((void**)&c->col, ((size_t)nnz + 16) * 4));
-            SALG_CUDA(cudaMalloc((void**)&c->val, ((size_t)nnz + 16) * es));
+            c->col = (uint32_t*)dev_alloc(ctx, ((size_t)nnz + 16) * 4);
+            c->val = dev_alloc(ctx, ((size_t)nnz + 16) * es);
             SALG_CUDA(cudaMemsetAsync(c->col + nnz, 0, 16 * 4, st));
             SALG_CUDA(cudaMemsetAsync((char*)c->val + (size_t)nnz * es, 0, 16 * es, st));
             if (nrows) {
@@ -153,7 +152,7 @@ extern "C" int salg_csr_synth(salg_ctx* ctx, int dtype, uint64_t seed, int64_t r
             }
             SALG_CUDA(cudaStreamSynchronize(st));
         } catch (...) {
-            if (ptr) cudaFree(ptr);
+            dev_free(ctx, ptr);
             if (c) csr_destroy(c);
             throw;
         }

@@ -52,11 +52,11 @@ struct TcTiles {
     int64_t nnz = 0;
 };
 
-void tc_free(void* p) {
+void tc_free(salg_ctx* owner, void* p) {
     TcTiles* t = (TcTiles*)p;
     if (!t) return;
-    if (t->entries) cudaFree(t->entries);
-    if (t->tile_ptr) cudaFree(t->tile_ptr);
+    dev_free(owner, t->entries);
+    dev_free(owner, t->tile_ptr);
     delete t;
 }
 
@@ -229,8 +229,8 @@ void* tc_build(salg_ctx* ctx, const salg_csr* c) {
         int64_t n_tiles = (int64_t)t->n_rb * t->n_cb;
         SALG_REQUIRE(n_tiles < ((int64_t)1 << 31), SALG_ERR_UNSUPPORTED, "too many tiles");
         ProfScope ps(ctx, PROF_TRANSPOSE, (double)c->nnz * (sizeof(T) + 4 + 8));
-        SALG_CUDA(cudaMalloc((void**)&t->entries, ((size_t)c->nnz + 1024) * sizeof(uint2)));
-        SALG_CUDA(cudaMalloc((void**)&t->tile_ptr, (size_t)(n_tiles + 2) * 8));
+        t->entries = (uint2*)dev_alloc(ctx, ((size_t)c->nnz + 1024) * sizeof(uint2));
+        t->tile_ptr = (int64_t*)dev_alloc(ctx, (size_t)(n_tiles + 2) * 8);
         SALG_CUDA(cudaMemsetAsync(t->entries + c->nnz, 0, 1024 * sizeof(uint2), st));
         DevBuf<unsigned> info(2, st);
         SALG_CUDA(cudaMemsetAsync(info.get(), 0, 8, st));
@@ -272,7 +272,7 @@ void* tc_build(salg_ctx* ctx, const salg_csr* c) {
         }
     } catch (...) {
         cudaStreamSynchronize(st);
-        tc_free(t);
+        tc_free(ctx, t);
         throw;
     }
     return t;
