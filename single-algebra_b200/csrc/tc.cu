@@ -41,10 +41,12 @@ constexpr int TC_RPAD = 4;            // row blocks are padded to a multiple of 
 constexpr int TC_SLOT_ENTRIES = 768;  // entries per ring slot (one tile); denser tiles read their tail from global memory
 constexpr int TC_SLOT_BYTES = (TC_SLOT_ENTRIES + 2) * 8;
 constexpr int TC_S_BYTES = 32768;     // sparse operand buffer: 256 x 64 (A X) or 128 x 128 (A^T Y) fp16
+constexpr int TC_NSB = 2;             // sparse operand buffers in flight (scatter runs up to 2 passes ahead of the MMA)
 constexpr uint32_t TC_SPIN_LIMIT = 1u << 24;
 
 struct TcTiles {
-    uint2* entries = nullptr;       // [nnz] .x = (local_row << 6) | local_col, .y = f32 bits of the value
+    uint2* entries = nullptr;       // [nnz] .x = half byte-offsets in the A X (bits 0-13) and A^T Y (bits 14-27) operand
+                                    //       buffers, .y = f32 bits of the value
     int64_t* tile_ptr = nullptr;    // [n_rb * n_cb + 1]
     int n_rb = 0, n_cb = 0;
     int a_terms = 2;                // 1 when every value is exact in fp16
@@ -196,7 +198,11 @@ __global__ void tc_keys_kernel(const int64_t* __restrict__ ptr, const uint32_t* 
             uint32_t c = col[p];
             float v = (float)val[p];
             keys[p] = rb * (uint32_t)n_cb + c / TC_CB;
-            payload[p] = make_uint2((lr << 6) | (c % TC_CB), __float_as_uint(v));
+            const uint32_t lc = c % TC_CB, cb = c / TC_CB;
+            // positions inside the 32 KB sparse-operand buffers of the two kernels (see tc_scatter_role)
+            const uint32_t off_ax = canon_off(lr + 128u * (rb & 1u), lc, 4096u) >> 1;
+            const uint32_t off_aty = canon_off(lc + 64u * (cb & 1u), lr, 2048u) >> 1;
+            payload[p] = make_uint2(off_ax | (off_aty << 14), __float_as_uint(v));
             bad |= (__half2float(__float2half_rn(v)) != v);
             amax = fmaxf(amax, fabsf(v));
         }
@@ -296,28 +302,38 @@ __global__ void tc_scale_kernel(const unsigned* __restrict__ amax_bits, float a_
 }
 // Panel P (n x 64 f32, row-major; row index = K of the product).  Block b covers K rows [b*KB, (b+1)*KB);
 // out[b] = canonical (M = 128: m = 2*column + term) x (K = KB) fp16 operand, 16 B K-chunks 2048 B apart.
+// One CTA converts 16 panel rows: coalesced 256 B row loads into shared memory, then thread m gathers the 8
+// K-values of its operand row and writes one 16 B chunk (128 threads x 16 B = one contiguous 2 KB K-chunk).
 template <int KB>
-__global__ void tc_prep_kernel(const float* __restrict__ P, int64_t n, int64_t n_blocks, const float* __restrict__ scales,
-                               unsigned short* __restrict__ out) {
-    // one thread per (k, 4 panel columns)
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t total = n_blocks * KB * 16;
-    if (i >= total) return;
+__global__ void __launch_bounds__(256)
+tc_prep_kernel(const float* __restrict__ P, int64_t n, int64_t n_blocks, const float* __restrict__ scales,
+               unsigned short* __restrict__ out) {
+    __shared__ float tile[16][LP + 1];
     const float s = scales[0];
-    int nq = (int)(i & 15);
-    int64_t k = i >> 4;
-    int64_t b = k / KB;
-    uint32_t kl = (uint32_t)(k % KB);
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (k < n) v = *reinterpret_cast<const float4*>(P + k * LP + nq * 4);
-    float x[4] = {v.x * s, v.y * s, v.z * s, v.w * s};
-    unsigned short* base = out + (size_t)b * (128 * KB);
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        uint32_t pc = (uint32_t)(nq * 4 + j);
-#pragma unroll
-        for (int t = 0; t < 2; t++) base[canon_off(2 * pc + t, kl, 2048u) >> 1] = f16_term(x[j], t);
+    const int64_t k0 = (int64_t)blockIdx.x * 16;
+    for (int i = threadIdx.x; i < 16 * LP; i += 256) {
+        int r = i >> 6, c = i & 63;
+        int64_t k = k0 + r;
+        tile[r][c] = (k < n) ? P[k * LP + c] * s : 0.f;
     }
+    __syncthreads();
+    const int half = threadIdx.x >> 7;          // which 8-row K-chunk of the 16 rows
+    const int m = threadIdx.x & 127;            // operand row: 2 * column + term
+    const int pc = m >> 1, t = m & 1;
+    const int64_t kc0 = k0 + half * 8;          // first K of this chunk
+    const int64_t b = kc0 / KB;
+    if (b >= n_blocks) return;
+    const uint32_t kl = (uint32_t)(kc0 % KB);
+    unsigned short h[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) h[j] = f16_term(tile[half * 8 + j][pc], t);
+    uint4 v;
+    v.x = h[0] | ((uint32_t)h[1] << 16);
+    v.y = h[2] | ((uint32_t)h[3] << 16);
+    v.z = h[4] | ((uint32_t)h[5] << 16);
+    v.w = h[6] | ((uint32_t)h[7] << 16);
+    unsigned short* base = out + (size_t)b * (128 * KB);
+    *reinterpret_cast<uint4*>(base + (canon_off((uint32_t)m, kl, 2048u) >> 1)) = v;
 }
 
 // ---- work sequences ---------------------------------------------------------------------------------------------------
@@ -337,7 +353,8 @@ struct TcSeq {
     __device__ __forceinline__ void tiles(int64_t s, int64_t& t0, int64_t& t1) const {
         if (!aty) {
             int64_t i = s / n_cb;
-            int cb = (int)(s - i * n_cb);
+            int cb = (int)(s - i * n_cb) + (int)(blockIdx.x % (unsigned)n_cb);   // staggered start: the CTAs do not all
+            if (cb >= n_cb) cb -= n_cb;                                          // pull the same panel slice from L2 at once
             int64_t g = (int64_t)blockIdx.x + i * gridDim.x;
             t0 = (2 * g) * n_cb + cb;
             t1 = (2 * g + 1) * n_cb + cb;
@@ -350,7 +367,7 @@ struct TcSeq {
     }
 };
 
-struct TcSlotMeta { long long e0[2]; int n[2]; int pad[2]; };   // per tile: first entry, entry count, leading pad (0/1)
+struct alignas(16) TcSlotMeta { long long e0[2]; int n[2]; int pad[2]; };   // per tile: first entry, entry count, leading pad (0/1)
 constexpr int TC_LOADER_WARPS = 4;   // entry loaders: warp w serves units s = w (mod 4), one lane each (a suspended
                                      // try_wait parks the whole warp, so lanes of one warp cannot wait independently)
 
@@ -359,7 +376,6 @@ template <int NS>
 __device__ __forceinline__ void tc_entry_loader(const uint2* __restrict__ entries, const int64_t* __restrict__ tile_ptr,
                                                 const TcSeq& seq, uint8_t* sRing, TcSlotMeta* sMeta, uint64_t* e_full,
                                                 uint64_t* e_free, int w) {
-    static_assert(NS % TC_LOADER_WARPS == 0, "a loader warp must always meet the same slots");
     const int64_t nu = seq.n_units();
     long long p[4] = {0, 0, 0, 0};       // tile pointers of the current unit: [e0, e1) of tile 0, [e0, e1) of tile 1
     bool two = false;
@@ -417,58 +433,67 @@ __device__ __forceinline__ void tc_entry_loader(const uint2* __restrict__ entrie
 // Operand coordinates: A X   n = 128*k + local_row (k = tile of the pair), K = local column, chunk stride 4096
 //                      A^T Y n =  64*k + local_col,                         K = local row,    chunk stride 2048
 template <bool ATY>
-__device__ __forceinline__ void tc_scatter_one(uint8_t* S, uint2 en, int k, float a_scale, int term) {
-    uint32_t lr = en.x >> 6, lc = en.x & 63u;
-    uint32_t off = ATY ? canon_off(lc + 64u * k, lr, 2048u) : canon_off(lr + 128u * k, lc, 4096u);
+__device__ __forceinline__ void tc_scatter_one(uint8_t* S, uint2 en, float a_scale, int term) {
+    const uint32_t off = ((ATY ? (en.x >> 14) : en.x) & 0x3FFFu) << 1;      // pre-computed at tile-build time
     *reinterpret_cast<unsigned short*>(S + off) = f16_term(__uint_as_float(en.y) * a_scale, term);
 }
 
 template <bool ATY, int NS>
 __device__ __forceinline__ void tc_scatter_role(const uint2* __restrict__ entries, int64_t n_units, int a_terms, float a_scale,
                                                 uint8_t* sS, const uint8_t* sRing, const TcSlotMeta* sMeta, uint64_t* e_full,
-                                                uint64_t* e_free, uint64_t* s_full, uint64_t* s_free, int tid) {
+                                                uint64_t* e_free, uint64_t* s_full, uint64_t* s_free, uint64_t* d_free, int units_per_d, int nb,
+                                                int tid) {
+    // d_free: the dense-operand stage of a finished group of `units_per_d` units is released here (by warp 0, when it
+    // sees the s_free of the group's last pass) instead of by a second tcgen05.commit of the single MMA thread
     const int lane = tid & 31;
     uint32_t pass = 0;
+    int slot = 0;
+    uint32_t slot_use = 0;
+    const uint32_t passes_per_d = (uint32_t)units_per_d * (uint32_t)a_terms;
     for (int64_t s = 0; s < n_units; s++) {
-        const int slot = (int)(s % NS);
+        const uint2* sl0 = reinterpret_cast<const uint2*>(sRing + (size_t)slot * (2 * TC_SLOT_BYTES));
+        const uint2* sl1 = reinterpret_cast<const uint2*>(sRing + (size_t)slot * (2 * TC_SLOT_BYTES) + TC_SLOT_BYTES);
         for (int term = 0; term < a_terms; term++) {
-            const int sb = pass & 1;
-            const uint32_t use = pass >> 1;
-            if (use > 0) mbar_wait_warp(&s_free[sb], (use - 1) & 1, lane);
+            const int sb = pass % TC_NSB;
+            const uint32_t use = pass / TC_NSB;
+            if (lane == 0) {
+                if (use > 0) {
+                    mbar_wait(&s_free[sb], (use - 1) & 1);
+                    // pass - TC_NSB has retired; if it closed a dense-operand group, hand that stage back to its loader
+                    const uint32_t done = pass - TC_NSB;
+                    if (tid == 0 && d_free && (done + 1) % passes_per_d == 0) mbar_arrive(&d_free[(done / passes_per_d) % nb]);
+                }
+                if (term == 0) mbar_wait(&e_full[slot], slot_use & 1);
+            }
+            __syncwarp();
             uint8_t* S = sS + sb * TC_S_BYTES;
 #pragma unroll
             for (int i = 0; i < TC_S_BYTES / 16 / TC_SCATTER_THREADS; i++)
                 reinterpret_cast<uint4*>(S)[i * TC_SCATTER_THREADS + tid] = make_uint4(0, 0, 0, 0);
-            if (term == 0) mbar_wait_warp(&e_full[slot], (uint32_t)(s / NS) & 1, lane);
-            // gather this thread's entries of both tiles first (independent shared-memory loads)
-            const int n0 = sMeta[slot].n[0], n1 = sMeta[slot].n[1];
-            const uint2* sl0 = reinterpret_cast<const uint2*>(sRing + (size_t)slot * (2 * TC_SLOT_BYTES)) + sMeta[slot].pad[0];
-            const uint2* sl1 = reinterpret_cast<const uint2*>(sRing + (size_t)slot * (2 * TC_SLOT_BYTES) + TC_SLOT_BYTES) +
-                               sMeta[slot].pad[1];
-            const int lim = TC_SLOT_ENTRIES - 1;     // entries guaranteed to sit in the slot whatever the pad
-            uint2 en[4];
-            bool ok[4];
-            ok[0] = tid < n0 && tid < lim;
-            ok[1] = tid + TC_SCATTER_THREADS < n0 && tid + TC_SCATTER_THREADS < lim;
-            ok[2] = tid < n1 && tid < lim;
-            ok[3] = tid + TC_SCATTER_THREADS < n1 && tid + TC_SCATTER_THREADS < lim;
-            en[0] = ok[0] ? sl0[tid] : make_uint2(0, 0);
-            en[1] = ok[1] ? sl0[tid + TC_SCATTER_THREADS] : make_uint2(0, 0);
-            en[2] = ok[2] ? sl1[tid] : make_uint2(0, 0);
-            en[3] = ok[3] ? sl1[tid + TC_SCATTER_THREADS] : make_uint2(0, 0);
+            // this thread's entries of both tiles (independent shared-memory loads, issued before the barrier)
+            const int4 mt = *reinterpret_cast<const int4*>(&sMeta[slot].n[0]);     // n0, n1, pad0, pad1
+            const int n0 = mt.x, n1 = mt.y;
+            constexpr int lim = TC_SLOT_ENTRIES - 1;     // entries guaranteed to sit in the slot whatever the pad
+            const bool ok0 = tid < n0, ok1 = tid + TC_SCATTER_THREADS < n0 && tid + TC_SCATTER_THREADS < lim;
+            const bool ok2 = tid < n1, ok3 = tid + TC_SCATTER_THREADS < n1 && tid + TC_SCATTER_THREADS < lim;
+            uint2 en0 = ok0 ? sl0[mt.z + tid] : make_uint2(0, 0);
+            uint2 en1 = ok1 ? sl0[mt.z + tid + TC_SCATTER_THREADS] : make_uint2(0, 0);
+            uint2 en2 = ok2 ? sl1[mt.w + tid] : make_uint2(0, 0);
+            uint2 en3 = ok3 ? sl1[mt.w + tid + TC_SCATTER_THREADS] : make_uint2(0, 0);
             named_bar_sync(1, TC_SCATTER_THREADS);       // every thread's clearing stores precede every scatter store
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-                if (ok[j]) tc_scatter_one<ATY>(S, en[j], j >> 1, a_scale, term);
-            // rare: tiles with more entries than two per thread / than the slot holds
-            for (int k = 0; k < 2; k++) {
-                const int n = k ? n1 : n0;
-                const uint2* sl = k ? sl1 : sl0;
-                const long long e0 = sMeta[slot].e0[k];
-                for (int i = tid; i < n; i += TC_SCATTER_THREADS) {
-                    if (i < lim && i < 2 * TC_SCATTER_THREADS) continue;      // handled above
-                    uint2 e = (i < lim) ? sl[i] : entries[e0 + i];
-                    tc_scatter_one<ATY>(S, e, k, a_scale, term);
+            if (ok0) tc_scatter_one<ATY>(S, en0, a_scale, term);
+            if (ok1) tc_scatter_one<ATY>(S, en1, a_scale, term);
+            if (ok2) tc_scatter_one<ATY>(S, en2, a_scale, term);
+            if (ok3) tc_scatter_one<ATY>(S, en3, a_scale, term);
+            if (n0 > lim || n1 > lim) {
+                // rare: a tile with more entries than two per thread / than the slot holds
+                for (int k = 0; k < 2; k++) {
+                    const int n = k ? n1 : n0;
+                    const uint2* sl = (k ? sl1 : sl0) + (k ? mt.w : mt.z);
+                    const long long e0 = sMeta[slot].e0[k];
+                    for (int i = tid + 2 * TC_SCATTER_THREADS; i < n; i += TC_SCATTER_THREADS)
+                        if (i < lim) tc_scatter_one<ATY>(S, sl[i], a_scale, term);
+                    for (int i = lim + tid; i < n; i += TC_SCATTER_THREADS) tc_scatter_one<ATY>(S, entries[e0 + i], a_scale, term);
                 }
             }
             fence_proxy_async();
@@ -479,27 +504,28 @@ __device__ __forceinline__ void tc_scatter_role(const uint2* __restrict__ entrie
             }
             pass++;
         }
+        if (++slot == NS) { slot = 0; slot_use++; }
     }
 }
 
 // ---- Y = A X - 1 corr^T -----------------------------------------------------------------------------------------------------
 struct AxSmem {
     static constexpr int D_BYTES = 128 * TC_CB * 2;          // 16 KB per stage: panel slice (M = 128) x (K = 64)
-    static constexpr int NB = 3;
+    static constexpr int NB = 4;                             // >= TC_NSB + 2: a stage is released TC_NSB passes late
     static constexpr int NS = 8;                             // ring slots (one unit = two tiles each)
-    static constexpr int TOTAL = 2 * TC_S_BYTES + NB * D_BYTES + NS * 2 * TC_SLOT_BYTES + 1024;
+    static constexpr int TOTAL = TC_NSB * TC_S_BYTES + NB * D_BYTES + NS * 2 * TC_SLOT_BYTES + 1024;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_ax_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ tile_ptr, int n_rb, int n_cb, int a_terms,
              float a_scale, int64_t nrows, const uint8_t* __restrict__ Xprep, const float* __restrict__ scales,
-             float* __restrict__ Y, const double* __restrict__ corr) {
+             float* __restrict__ Y, const double* __restrict__ corr, int dbg) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sS = smem;
-    uint8_t* sD = sS + 2 * TC_S_BYTES;
+    uint8_t* sD = sS + TC_NSB * TC_S_BYTES;
     uint8_t* sRing = sD + AxSmem::NB * AxSmem::D_BYTES;
-    __shared__ uint64_t s_full[2], s_free[2], d_full[AxSmem::NB], d_free[AxSmem::NB], acc_full[2], acc_free[2];
+    __shared__ uint64_t s_full[TC_NSB], s_free[TC_NSB], d_full[AxSmem::NB], d_free[AxSmem::NB], acc_full[2], acc_free[2];
     __shared__ uint64_t e_full[AxSmem::NS], e_free[AxSmem::NS];
     __shared__ TcSlotMeta sMeta[AxSmem::NS];
     __shared__ uint32_t s_tmem;
@@ -508,9 +534,11 @@ tc_ax_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ tile
     const int n_pairs = n_rb / 2;
     const int n_mine = ((int)blockIdx.x < n_pairs) ? (n_pairs - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     if (tid == 0) {
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < TC_NSB; i++) {
             mbar_init(&s_full[i], TC_SCATTER_WARPS);
             mbar_init(&s_free[i], 1);
+        }
+        for (int i = 0; i < 2; i++) {
             mbar_init(&acc_full[i], 1);
             mbar_init(&acc_free[i], 4);
         }
@@ -533,7 +561,7 @@ tc_ax_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ tile
 
     if (warp < TC_SCATTER_WARPS) {
         tc_scatter_role<false, AxSmem::NS>(entries, seq.n_units(), a_terms, a_scale, sS, sRing, sMeta, e_full, e_free, s_full,
-                                           s_free, tid);
+                                           s_free, nullptr, 1, 1, tid);
     } else if (warp >= TC_W_ELOAD) {
         if (lane == 0) tc_entry_loader<AxSmem::NS>(entries, tile_ptr, seq, sRing, sMeta, e_full, e_free, warp - TC_W_ELOAD);
     } else if (warp == TC_W_BLOAD) {
@@ -545,8 +573,11 @@ tc_ax_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ tile
                     const int bb = it % AxSmem::NB;
                     const uint32_t use = it / AxSmem::NB;
                     if (use > 0) mbar_wait(&d_free[bb], (use - 1) & 1);
+                    int cbr = cb + (int)(blockIdx.x % (unsigned)n_cb);      // same staggered order as TcSeq::tiles
+                    if (cbr >= n_cb) cbr -= n_cb;
+                    if (dbg & 4) { mbar_arrive(&d_full[bb]); continue; }
                     mbar_expect_tx(&d_full[bb], AxSmem::D_BYTES);
-                    bulk_g2s(sD + bb * AxSmem::D_BYTES, Xprep + (size_t)cb * AxSmem::D_BYTES, AxSmem::D_BYTES, &d_full[bb]);
+                    bulk_g2s(sD + bb * AxSmem::D_BYTES, Xprep + (size_t)cbr * AxSmem::D_BYTES, AxSmem::D_BYTES, &d_full[bb]);
                 }
             }
         }
@@ -554,8 +585,8 @@ tc_ax_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ tile
         // ================= MMA issuer =================
         if (lane == 0) {
             uint32_t pass = 0, it = 0;
-            uint64_t s_desc[2], d_desc[AxSmem::NB];
-            for (int i = 0; i < 2; i++) s_desc[i] = umma_desc(smem_u32(sS + i * TC_S_BYTES), 4096, 128);
+            uint64_t s_desc[TC_NSB], d_desc[AxSmem::NB];
+            for (int i = 0; i < TC_NSB; i++) s_desc[i] = umma_desc(smem_u32(sS + i * TC_S_BYTES), 4096, 128);
             for (int i = 0; i < AxSmem::NB; i++) d_desc[i] = umma_desc(smem_u32(sD + i * AxSmem::D_BYTES), 2048, 128);
             constexpr uint32_t idesc = tc_idesc(256);
             long long c_acc = 0, c_d = 0, c_s = 0, c_issue = 0, c_commit = 0, t_prev = clock64(), t_begin = t_prev;
@@ -570,8 +601,8 @@ tc_ax_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ tile
                     mbar_wait(&d_full[bb], (it / AxSmem::NB) & 1);
                     TC_T(c_d);
                     for (int term = 0; term < a_terms; term++) {
-                        const int sb = pass & 1;
-                        mbar_wait(&s_full[sb], (pass >> 1) & 1);
+                        const int sb = pass % TC_NSB;
+                        mbar_wait(&s_full[sb], (pass / TC_NSB) & 1);
                         tc_fence_after();
                         TC_T(c_s);
                         // K = 64: four K-steps; dense operand advances 2 chunks x 2048 B, sparse operand 2 x 4096 B
@@ -633,7 +664,7 @@ struct AtySmem {
     static constexpr int NB = 2;
     static constexpr int NS = 8;                             // ring slots (one unit = two tiles each)
     static constexpr int G = 8;                               // operator column blocks per CTA: 4 units x 128 TMEM columns
-    static constexpr int TOTAL = 2 * TC_S_BYTES + NB * D_BYTES + NS * 2 * TC_SLOT_BYTES + 1024;
+    static constexpr int TOTAL = TC_NSB * TC_S_BYTES + NB * D_BYTES + NS * 2 * TC_SLOT_BYTES + 1024;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -643,9 +674,9 @@ tc_aty_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ til
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sS = smem;
-    uint8_t* sD = sS + 2 * TC_S_BYTES;
+    uint8_t* sD = sS + TC_NSB * TC_S_BYTES;
     uint8_t* sRing = sD + AtySmem::NB * AtySmem::D_BYTES;
-    __shared__ uint64_t s_full[2], s_free[2], d_full[AtySmem::NB], d_free[AtySmem::NB], acc_full;
+    __shared__ uint64_t s_full[TC_NSB], s_free[TC_NSB], d_full[AtySmem::NB], d_free[AtySmem::NB], acc_full;
     __shared__ uint64_t e_full[AtySmem::NS], e_free[AtySmem::NS];
     __shared__ TcSlotMeta sMeta[AtySmem::NS];
     __shared__ uint32_t s_tmem;
@@ -660,7 +691,7 @@ tc_aty_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ til
     const int n_units = (ntr + 1) / 2;
 
     if (tid == 0) {
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < TC_NSB; i++) {
             mbar_init(&s_full[i], TC_SCATTER_WARPS);
             mbar_init(&s_free[i], 1);
         }
@@ -686,7 +717,7 @@ tc_aty_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ til
     if (warp < TC_SCATTER_WARPS) {
         if (active)
             tc_scatter_role<true, AtySmem::NS>(entries, seq.n_units(), a_terms, a_scale, sS, sRing, sMeta, e_full, e_free, s_full,
-                                               s_free, tid);
+                                               s_free, nullptr, 1, 1, tid);
     } else if (warp >= TC_W_ELOAD) {
         if (active && lane == 0)
             tc_entry_loader<AtySmem::NS>(entries, tile_ptr, seq, sRing, sMeta, e_full, e_free, warp - TC_W_ELOAD);
@@ -704,8 +735,8 @@ tc_aty_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ til
     } else if (warp == TC_W_MMA) {
         if (lane == 0 && active) {
             uint32_t pass = 0, it = 0;
-            uint64_t s_desc[2], d_desc[AtySmem::NB];
-            for (int i = 0; i < 2; i++) s_desc[i] = umma_desc(smem_u32(sS + i * TC_S_BYTES), 2048, 128);
+            uint64_t s_desc[TC_NSB], d_desc[AtySmem::NB];
+            for (int i = 0; i < TC_NSB; i++) s_desc[i] = umma_desc(smem_u32(sS + i * TC_S_BYTES), 2048, 128);
             for (int i = 0; i < AtySmem::NB; i++) d_desc[i] = umma_desc(smem_u32(sD + i * AtySmem::D_BYTES), 2048, 128);
             constexpr uint32_t idesc = tc_idesc(128);
             for (int rb = rb0; rb < rb1; rb++, it++) {
@@ -714,8 +745,8 @@ tc_aty_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ til
                 for (int u = 0; u < n_units; u++) {
                     const uint32_t d_tmem = tmem_base + (uint32_t)u * 128u;
                     for (int term = 0; term < a_terms; term++) {
-                        const int sb = pass & 1;
-                        mbar_wait(&s_full[sb], (pass >> 1) & 1);
+                        const int sb = pass % TC_NSB;
+                        mbar_wait(&s_full[sb], (pass / TC_NSB) & 1);
                         tc_fence_after();
                         // K = 128 rows: eight K-steps, both operands advance 2 chunks x 2048 B per step
                         umma_f16_run4(d_tmem, d_desc[bb], s_desc[sb], idesc, ((rb - rb0) | term) != 0, 256, 256);
@@ -724,7 +755,7 @@ tc_aty_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ til
                         pass++;
                     }
                 }
-                umma_commit(&d_free[bb]);
+                umma_commit(&d_free[bb]);      // once per row block (amortised over the block's units)
             }
             umma_commit(&acc_full);
         }
@@ -786,8 +817,7 @@ static void tc_prepare_panel(salg_ctx* ctx, const float* P, int64_t n, int64_t n
     }
     tc_scale_kernel<<<1, 1, 0, st>>>(d_amax, a_scale, d_scales);
     ctx->n_launch++;
-    int64_t total = n_blocks * KB * 16;
-    tc_prep_kernel<KB><<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(P, n, n_blocks, d_scales, (unsigned short*)out);
+    tc_prep_kernel<KB><<<(unsigned)ceil_div(n_blocks * KB, 16), 256, 0, st>>>(P, n, n_blocks, d_scales, (unsigned short*)out);
     ctx->n_launch++;
     SALG_CUDA(cudaGetLastError());
 }
@@ -819,7 +849,7 @@ void tc_spmm_A(salg_ctx* ctx, const salg_csr* c, const float* X, float* Y, const
     int n_pairs = t->n_rb / 2;
     int grid = n_pairs < ctx->sm_count ? n_pairs : ctx->sm_count;
     tc_ax_kernel<<<grid, TC_THREADS, AxSmem::TOTAL, st>>>(t->entries, t->tile_ptr, t->n_rb, t->n_cb, t->a_terms, t->a_scale,
-                                                          c->nrows, Xprep.get(), scales.get(), Y, corr);
+                                                          c->nrows, Xprep.get(), scales.get(), Y, corr, getenv("SALG_TC_DBG") ? atoi(getenv("SALG_TC_DBG")) : 0);
     ctx->n_launch++;
     SALG_CUDA(cudaGetLastError());
     tc_dbg_print(ctx, "ax");
