@@ -96,81 +96,106 @@ void panel_gram(salg_ctx* ctx, const T* P, int64_t m, double* d_out) {
 template void panel_gram<float>(salg_ctx*, const float*, int64_t, double*);
 template void panel_gram<double>(salg_ctx*, const double*, int64_t, double*);
 
-// ---- Cholesky G = R^T R of the leading k x k block, R^{-1}; one CTA ---------------------------------------
-// Pivots that are not safely positive are floored (rank-deficient panels: l > rank(A)); flag bit 1 is
-// raised, the caller's second CholeskyQR pass re-orthonormalises the affected directions.
+// ---- Cholesky G = R^T R of the leading k x k block, R^{-1}; one CTA of 64 threads ---------------------------------
+// Right-looking Cholesky: thread i keeps row i of the trailing matrix in REGISTERS; the column loop is a runtime
+// loop (small code: straight-line unrolling of all 64 columns was instruction-fetch bound), the 64-wide trailing
+// update inside it is unrolled with static register indices and predicates.  The triangular inverse keeps column
+// c of R^{-1} in registers the same way.  This kernel is replicated on every GPU of a row-sharded run and runs ~20
+// times per fit, so its latency is serial time at any GPU count (first version: 90 us per call).
+// Pivots that are not safely positive are floored (rank-deficient panels: l > rank(A)); flag bit 1 is raised, the
+// caller's second CholeskyQR pass re-orthonormalises the affected directions.
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(64)
 chol_inv_kernel(const double* __restrict__ G, int k, double* __restrict__ R, double* __restrict__ Rinv,
                 T* __restrict__ RinvT, int* __restrict__ flag) {
-    extern __shared__ __align__(16) unsigned char dyn_smem[];
-    double (*L)[LP + 1] = reinterpret_cast<double (*)[LP + 1]>(dyn_smem);            // lower factor, G = L L^T; R = L^T
-    double (*X)[LP + 1] = L + LP;                                                    // R^{-1} (upper)
-    __shared__ double s_maxdiag;
-    const int tid = threadIdx.x;
-    for (int i = tid; i < LP * LP; i += 256) {
-        int r = i >> 6, c = i & 63;
-        L[r][c] = (r < k && c < k) ? G[r * LP + c] : (r == c ? 1.0 : 0.0);
-        X[r][c] = 0.0;
-    }
-    __syncthreads();
-    if (tid == 0) {
+    __shared__ double Ls[LP][LP + 1];     // L (lower), identity outside the leading k x k block
+    __shared__ double col[LP];            // current column of L, broadcast to every thread
+    __shared__ double s_md[2], s_piv;
+    const int i = threadIdx.x;            // this thread owns row i of L and column i of R^{-1}
+    double row[LP];
+#pragma unroll
+    for (int c = 0; c < LP; c++) row[c] = (i < k && c < k && c <= i) ? G[i * LP + c] : 0.0;
+    {
         double md = 0.0;
-        for (int i = 0; i < k; i++) md = fmax(md, L[i][i]);
-        s_maxdiag = md > 0.0 ? md : 1.0;
+#pragma unroll
+        for (int c = 0; c < LP; c++) if (c == i) md = row[c];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) md = fmax(md, __shfl_xor_sync(0xFFFFFFFFu, md, o));
+        if ((i & 31) == 0) s_md[i >> 5] = md;
     }
     __syncthreads();
-    const double floor_piv = s_maxdiag * 1e-13;
+    const double mdiag = fmax(s_md[0], s_md[1]);
+    const double floor_piv = (mdiag > 0.0 ? mdiag : 1.0) * 1e-13;
+    bool bad = false;
     for (int j = 0; j < k; j++) {
-        if (tid == 0) {
-            double p = L[j][j];
-            if (!(p > floor_piv)) {
-                p = floor_piv;
-                atomicOr(flag, 1);
+        // row[j] of thread j is the pivot; of threads i > j the not-yet-scaled L[i][j]
+        double rj = 0.0;
+#pragma unroll
+        for (int c = 0; c < LP; c++) if (c == j) rj = row[c];
+        if (i == j) {
+            if (!(rj > floor_piv)) {
+                rj = floor_piv;
+                bad = true;
             }
-            L[j][j] = sqrt(p);
+            s_piv = sqrt(rj);
         }
         __syncthreads();
-        const double d = L[j][j];
-        for (int i = j + 1 + tid; i < k; i += 256) L[i][j] /= d;
+        const double d = s_piv;
+        const double lij = (i == j) ? d : ((i > j && i < k) ? rj / d : 0.0);
+        col[i] = lij;                    // (all threads left the previous update loop before the barrier above)
+        Ls[i][j] = lij;
         __syncthreads();
-        // trailing update of the lower triangle: L[i][c] -= L[i][j] * L[c][j], j < c <= i < k
-        const int n = k - j - 1;
-        for (int t = tid; t < n * n; t += 256) {
-            int i = j + 1 + t / n, c = j + 1 + t % n;
-            if (c <= i) L[i][c] -= L[i][j] * L[c][j];
+        // trailing update: row[c] -= L[i][j] * L[c][j] for j < c <= i
+#pragma unroll
+        for (int c = 0; c < LP; c++) {
+            const double lcj = col[c];
+            if (c > j && c <= i) row[c] = fma(-lij, lcj, row[c]);
         }
-        __syncthreads();
     }
-    // R = L^T (upper); solve R X = I column by column (thread c owns column c of X)
-    if (tid < LP) {
-        const int c = tid;
-        if (c < k) {
-            for (int i = c; i >= 0; i--) {
-                double s = (i == c) ? 1.0 : 0.0;
-                for (int t = i + 1; t <= c; t++) s -= L[t][i] * X[t][c];   // R[i][t] = L[t][i]
-                X[i][c] = s / L[i][i];
-            }
-        } else {
-            X[c][c] = 1.0;
-        }
+    if (bad) atomicOr(flag, 1);
+    // identity outside the leading block (rows >= k entirely; columns >= k of rows < k)
+#pragma unroll 1
+    for (int c = 0; c < LP; c++) {
+        if (i >= k) Ls[i][c] = (c == i) ? 1.0 : 0.0;
+        else if (c >= k) Ls[i][c] = 0.0;
     }
     __syncthreads();
-    for (int i = tid; i < LP * LP; i += 256) {
-        int r = i >> 6, c = i & 63;
-        double rv = (r < k && c < k) ? (c >= r ? L[c][r] : 0.0) : (r == c ? 1.0 : 0.0);
-        if (R) R[i] = rv;
-        if (Rinv) Rinv[i] = X[r][c];
-        if (RinvT) RinvT[i] = (T)X[r][c];
+    // R = L^T (upper).  Column i of X = R^{-1}: X[r][i] = (delta_ri - sum_{t>r} R[r][t] X[t][i]) / R[r][r],
+    // R[r][t] = L[t][r] broadcast from shared memory, X[.][i] in registers (zero below the diagonal: t > i).
+    double x[LP];
+#pragma unroll
+    for (int r = 0; r < LP; r++) x[r] = 0.0;
+    for (int r = LP - 1; r >= 0; r--) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+        for (int t = 0; t < LP; t += 4) {
+            a0 = fma(Ls[t][r], x[t], a0);            // entries with t <= r are zero in L^T's row r ... except t == r
+            a1 = fma(Ls[t + 1][r], x[t + 1], a1);
+            a2 = fma(Ls[t + 2][r], x[t + 2], a2);
+            a3 = fma(Ls[t + 3][r], x[t + 3], a3);
+        }
+        // x[t] is still 0 for every t <= r at this point (filled from the bottom up), so the sum covers t > r only
+        const double num = ((r == i) ? 1.0 : 0.0) - ((a0 + a1) + (a2 + a3));
+        const double xr = (r <= i) ? num / Ls[r][r] : 0.0;
+#pragma unroll
+        for (int t = 0; t < LP; t++) if (t == r) x[t] = xr;
+    }
+    // outputs: thread i writes column i of Rinv / RinvT and column i of R (R[r][i] = L[i][r])
+#pragma unroll 1
+    for (int r = 0; r < LP; r++) {
+        double xr = 0.0;
+#pragma unroll
+        for (int t = 0; t < LP; t++) if (t == r) xr = x[t];
+        if (Rinv) Rinv[r * LP + i] = xr;
+        if (RinvT) RinvT[r * LP + i] = (T)xr;
+        if (R) R[r * LP + i] = (r <= i) ? Ls[i][r] : 0.0;
     }
 }
 
 template <typename T>
 void chol_inv(salg_ctx* ctx, const double* d_G, int k, double* d_R, double* d_Rinv, T* d_RinvT, int* d_flag) {
     ProfScope ps(ctx, PROF_CHOL, 0.0);
-    constexpr int kSmem = 2 * LP * (LP + 1) * 8;
-    SALG_CUDA(cudaFuncSetAttribute(chol_inv_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    chol_inv_kernel<T><<<1, 256, kSmem, ctx->stream>>>(d_G, k, d_R, d_Rinv, d_RinvT, d_flag);
+    chol_inv_kernel<T><<<1, 64, 0, ctx->stream>>>(d_G, k, d_R, d_Rinv, d_RinvT, d_flag);
     ctx->n_launch++;
     SALG_CUDA(cudaGetLastError());
 }

@@ -212,7 +212,7 @@ static salg_pca* pca_fit(salg_ctx* ctx, const salg_csr* x, const salg_pca_params
                 }
                 spmm_At<T>(ctx, op, Y.get(), Z.get(), d_mu, center ? cs.get() : nullptr);
                 allreduce_panel_T<T>(ctx, Z.get(), (size_t)n_eff * LP, center ? d_mu : nullptr, cs.get(), n_eff);
-                cholqr2<T>(ctx, Z.get(), n_eff, l, false, nullptr, nullptr, d_flag.get(), 2);
+                cholqr2<T>(ctx, Z.get(), n_eff, l, false, nullptr, nullptr, d_flag.get(), 1);   // intermediate: one pass
                 if (center) panel_colsum<T>(ctx, Z.get(), n_eff, d_mu, corr.get());
                 spmm_A<T>(ctx, op, Z.get(), Y.get(), center ? corr.get() : nullptr, false);
             }

@@ -123,9 +123,16 @@ col_stats_tiled_kernel(const int64_t* __restrict__ ptr, const uint32_t* __restri
                     uint32_t c = cc[u] - c0;
                     A x = (A)vv[u];
                     smem_add(&acc[2 * c], x);
-                    smem_add(&acc[2 * c + 1], x * x);
+                    if (keepbits) {
+                        // masked fit: sum of squares is only needed for the kept columns (total_var,
+                        // pca/sparse_masked/mod.rs:303-307) -> one shared-memory atomic per entry instead of two
+                        const unsigned kbit = (kb[cc[u] >> 5] >> (cc[u] & 31)) & 1u;
+                        kept += kbit;
+                        if (kbit) smem_add(&acc[2 * c + 1], x * x);
+                    } else {
+                        smem_add(&acc[2 * c + 1], x * x);
+                    }
                     if (CNT) atomicAdd(&cnt[c], 1u);
-                    if (keepbits) kept += (kb[cc[u] >> 5] >> (cc[u] & 31)) & 1u;
                 }
             }
         }

@@ -98,3 +98,21 @@ def test_tc_products_match_chunk_kernels_and_f64(salg, ctx):
             assert np.abs(got_ch - ref).max() <= 2e-5 * scale
             # the split-bf16 tensor-core product is as accurate as the f32 FMA chain
             assert np.abs(got_tc - ref).max() <= 4 * np.abs(got_ch - ref).max() + 1e-6 * scale
+
+
+def test_tc_products_dense_tiles_and_tiny_shapes(salg, ctx):
+    """Tiles denser than a ring slot (fully dense blocks: 8192 entries per 128 x 64 tile) take the overflow path of
+    the scatter role; tiny shapes exercise padding (rows < 128, columns < 64)."""
+    rng = np.random.default_rng(9)
+    for shape, dens in (((300, 200), 1.0), ((257, 130), 0.6), ((5, 3), 1.0), ((1, 70), 0.5)):
+        D = rng.integers(1, 9, size=shape).astype(np.float32) * (rng.random(shape) < dens)
+        D[0, 0] = 3.0
+        A = sp.csr_matrix(D)
+        d = salg.CsrMatrix.from_scipy(A, ctx).to_device()
+        mu = np.asarray(A.mean(axis=0)).ravel().astype(np.float32)
+        ctx.set_spmm_impl("tc")
+        for transposed in (False, True):
+            X = rng.standard_normal((shape[0] if transposed else shape[1], 60)).astype(np.float32)
+            ref = _ref_products(A, X, mu, transposed)
+            got = salg.op_spmm(d, X, mu=mu, transposed=transposed)
+            assert np.abs(got - ref).max() <= 2e-5 * max(np.abs(ref).max(), 1e-30), (shape, dens, transposed)
