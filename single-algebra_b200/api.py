@@ -471,15 +471,17 @@ class _PCABase:
         N.check(getattr(lib, f"salg_pca_transform_{sfx}")(d.ctx._h, self._model, d._h, self.transform_mode, N.ptr(out)))
         return out
 
-    def fit_transform(self, x, omega=None):
+    def fit_transform(self, x, omega=None, out=None):
         """`fit_transform(&mut self, x)` (pca/sparse/mod.rs:355-358): fit, then the projection of the
         same rows; the projection runs inside the fit call while the compacted operator is resident."""
         self._fit(x, omega, keep_scores=True)
         lib = N.load()
         sfx = "f64" if self._dtype == np.float64 else "f32"
         d = _as_device(x)
-        out = np.empty((d.nrows, self.components_.shape[0]), self._dtype)
-        N.check(getattr(lib, f"salg_pca_fit_scores_{sfx}")(self._ctx._h, self._model, N.ptr(out)))
+        if out is None:
+            out = np.empty((d.nrows, self.components_.shape[0]), self._dtype)
+        assert out.shape == (d.nrows, self.components_.shape[0]) and out.dtype == self._dtype
+        N.check(getattr(lib, f"salg_pca_fit_scores_{sfx}")(self._ctx._h, self._model, N.ptr(out)))   # `out` may be pinned
         return out
 
     def feature_importances(self):

@@ -14,7 +14,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 panel_gram_kernel(const T* __restrict__ P, int64_t m, double* __restrict__ out) {
     constexpr int TR = 32;                       // rows per tile
-    __shared__ T tile[TR][LP + 2];
+    __shared__ __align__(16) T tile[TR][LP + 4];   // row stride 68 elements: 16 B aligned rows, conflict-free float4 reads
     const int tid = threadIdx.x;
     const int ti = tid >> 4, tj = tid & 15;      // 16 x 16 threads, 4 x 4 outputs each
     double acc[4][4];
@@ -41,12 +41,9 @@ panel_gram_kernel(const T* __restrict__ P, int64_t m, double* __restrict__ out) 
                 for (int y = 0; y < 4; y++) p[x][y] = 0.f;
 #pragma unroll 8
             for (int r = 0; r < TR; r++) {
-                float a[4], b[4];
-#pragma unroll
-                for (int x = 0; x < 4; x++) {
-                    a[x] = (float)tile[r][4 * ti + x];
-                    b[x] = (float)tile[r][4 * tj + x];
-                }
+                const float4 av = *reinterpret_cast<const float4*>(&tile[r][4 * ti]);
+                const float4 bv = *reinterpret_cast<const float4*>(&tile[r][4 * tj]);
+                const float a[4] = {av.x, av.y, av.z, av.w}, b[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
                 for (int x = 0; x < 4; x++)
 #pragma unroll
@@ -110,7 +107,8 @@ chol_inv_kernel(const double* __restrict__ G, int k, double* __restrict__ R, dou
                 T* __restrict__ RinvT, int* __restrict__ flag) {
     __shared__ double Ls[LP][LP + 1];     // L (lower), identity outside the leading k x k block
     __shared__ double col[LP];            // current column of L, broadcast to every thread
-    __shared__ double s_md[2], s_piv;
+    __shared__ double dinv[LP];           // 1 / L[j][j]
+    __shared__ double s_md[2], s_dinv;
     const int i = threadIdx.x;            // this thread owns row i of L and column i of R^{-1}
     double row[LP];
 #pragma unroll
@@ -127,30 +125,33 @@ chol_inv_kernel(const double* __restrict__ G, int k, double* __restrict__ R, dou
     const double mdiag = fmax(s_md[0], s_md[1]);
     const double floor_piv = (mdiag > 0.0 ? mdiag : 1.0) * 1e-13;
     bool bad = false;
+    double cur = row[0];                  // row[j] of the column about to be processed (carried, no 64-way select)
     for (int j = 0; j < k; j++) {
-        // row[j] of thread j is the pivot; of threads i > j the not-yet-scaled L[i][j]
-        double rj = 0.0;
-#pragma unroll
-        for (int c = 0; c < LP; c++) if (c == j) rj = row[c];
         if (i == j) {
-            if (!(rj > floor_piv)) {
-                rj = floor_piv;
+            double p = cur;
+            if (!(p > floor_piv)) {
+                p = floor_piv;
                 bad = true;
             }
-            s_piv = sqrt(rj);
+            cur = p;
+            s_dinv = rsqrt(p);            // the pivot chain is the serial part: reciprocal square root, no divide
         }
         __syncthreads();
-        const double d = s_piv;
-        const double lij = (i == j) ? d : ((i > j && i < k) ? rj / d : 0.0);
-        col[i] = lij;                    // (all threads left the previous update loop before the barrier above)
+        const double di = s_dinv;
+        const double lij = (i == j) ? cur * di : ((i > j && i < k) ? cur * di : 0.0);
+        col[i] = lij;                     // (all threads left the previous update loop before the barrier above)
         Ls[i][j] = lij;
+        if (i == j) dinv[j] = di;
         __syncthreads();
-        // trailing update: row[c] -= L[i][j] * L[c][j] for j < c <= i
+        // trailing update: row[c] -= L[i][j] * L[c][j] for j < c <= i; keep the next column's entry at hand
+        double nxt = 0.0;
 #pragma unroll
         for (int c = 0; c < LP; c++) {
             const double lcj = col[c];
             if (c > j && c <= i) row[c] = fma(-lij, lcj, row[c]);
+            if (c == j + 1) nxt = row[c];
         }
+        cur = nxt;
     }
     if (bad) atomicOr(flag, 1);
     // identity outside the leading block (rows >= k entirely; columns >= k of rows < k)
@@ -159,6 +160,7 @@ chol_inv_kernel(const double* __restrict__ G, int k, double* __restrict__ R, dou
         if (i >= k) Ls[i][c] = (c == i) ? 1.0 : 0.0;
         else if (c >= k) Ls[i][c] = 0.0;
     }
+    if (i >= k) dinv[i] = 1.0;
     __syncthreads();
     // R = L^T (upper).  Column i of X = R^{-1}: X[r][i] = (delta_ri - sum_{t>r} R[r][t] X[t][i]) / R[r][r],
     // R[r][t] = L[t][r] broadcast from shared memory, X[.][i] in registers (zero below the diagonal: t > i).
@@ -169,25 +171,22 @@ chol_inv_kernel(const double* __restrict__ G, int k, double* __restrict__ R, dou
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
         for (int t = 0; t < LP; t += 4) {
-            a0 = fma(Ls[t][r], x[t], a0);            // entries with t <= r are zero in L^T's row r ... except t == r
+            a0 = fma(Ls[t][r], x[t], a0);
             a1 = fma(Ls[t + 1][r], x[t + 1], a1);
             a2 = fma(Ls[t + 2][r], x[t + 2], a2);
             a3 = fma(Ls[t + 3][r], x[t + 3], a3);
         }
         // x[t] is still 0 for every t <= r at this point (filled from the bottom up), so the sum covers t > r only
         const double num = ((r == i) ? 1.0 : 0.0) - ((a0 + a1) + (a2 + a3));
-        const double xr = (r <= i) ? num / Ls[r][r] : 0.0;
+        const double xr = (r <= i) ? num * dinv[r] : 0.0;
 #pragma unroll
         for (int t = 0; t < LP; t++) if (t == r) x[t] = xr;
     }
-    // outputs: thread i writes column i of Rinv / RinvT and column i of R (R[r][i] = L[i][r])
-#pragma unroll 1
-    for (int r = 0; r < LP; r++) {
-        double xr = 0.0;
+    // outputs: thread i writes column i of Rinv / RinvT / R (consecutive threads -> consecutive addresses)
 #pragma unroll
-        for (int t = 0; t < LP; t++) if (t == r) xr = x[t];
-        if (Rinv) Rinv[r * LP + i] = xr;
-        if (RinvT) RinvT[r * LP + i] = (T)xr;
+    for (int r = 0; r < LP; r++) {
+        if (Rinv) Rinv[r * LP + i] = x[r];
+        if (RinvT) RinvT[r * LP + i] = (T)x[r];
         if (R) R[r * LP + i] = (r <= i) ? Ls[i][r] : 0.0;
     }
 }
@@ -230,10 +229,17 @@ panel_mul_kernel(const T* P, int64_t m, const T* __restrict__ M, T* out) {
 #pragma unroll 8
         for (int kk = 0; kk < LP; kk++) {
             T a[4], b[4];
+            if (sizeof(T) == 4) {
+                const float4 av = *reinterpret_cast<const float4*>(&Pt[kk][4 * ty]);
+                const float4 bv = *reinterpret_cast<const float4*>(&Ms[kk][4 * tx]);
+                a[0] = (T)av.x; a[1] = (T)av.y; a[2] = (T)av.z; a[3] = (T)av.w;
+                b[0] = (T)bv.x; b[1] = (T)bv.y; b[2] = (T)bv.z; b[3] = (T)bv.w;
+            } else {
 #pragma unroll
-            for (int x = 0; x < 4; x++) {
-                a[x] = Pt[kk][4 * ty + x];
-                b[x] = Ms[kk][4 * tx + x];
+                for (int x = 0; x < 4; x++) {
+                    a[x] = Pt[kk][4 * ty + x];
+                    b[x] = Ms[kk][4 * tx + x];
+                }
             }
 #pragma unroll
             for (int x = 0; x < 4; x++)
@@ -371,9 +377,13 @@ jacobi_svd64_kernel(const double* __restrict__ A, int k, double* __restrict__ U,
                     gamma += __shfl_xor_sync(0xFFFFFFFFu, gamma, o);
                 }
                 if (fabs(gamma) > tol * sqrt(alpha * beta) && gamma != 0.0) {
-                    double zeta = (beta - alpha) / (2.0 * gamma);
-                    double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                    double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+                    // rotation from fast reciprocal / reciprocal-square-root intrinsics: the 59 rounds x ~8 sweeps are a
+                    // serial chain, divisions and square roots were most of its latency
+                    double zeta = (beta - alpha) * __drcp_rn(2.0 * gamma);
+                    double h2 = fma(zeta, zeta, 1.0);
+                    double w = h2 * rsqrt(h2);                                   // sqrt(1 + zeta^2)
+                    double t = (zeta >= 0.0 ? 1.0 : -1.0) * __drcp_rn(fabs(zeta) + w);
+                    double c = rsqrt(fma(t, t, 1.0)), s = c * t;
                     W[p][lane] = c * wp0 - s * wq0;
                     W[p][lane + 32] = c * wp1 - s * wq1;
                     W[q][lane] = s * wp0 + c * wq0;
