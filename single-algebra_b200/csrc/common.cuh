@@ -236,10 +236,11 @@ void exclusive_scan_i64(salg_ctx* ctx, const int64_t* in, int64_t* out, int64_t 
 // ---- stats.cu -------------------------------------------------------------------------------------
 // column sums / sums of squares / stored-entry counts in f64 on the device (zeroed here; all-reduced
 // over the ranks of a row-sharded context)
-// keepbits (ncols bits) + row_kept [nrows+1]: also count, per row, the entries in kept columns (the compaction's
-// count pass fused into the statistics pass)
+// keepbits (ceil(ncols/32) mask words followed by as many exclusive prefix popcounts; n_kept set bits) + row_kept
+// [nrows+1]: also count, per row, the entries in kept columns (the compaction's count pass fused into the statistics pass)
 template <typename T> void col_stats_device(salg_ctx* ctx, const salg_csr* c, double* d_sum, double* d_sumsq, double* d_cnt,
-                                            const uint32_t* keepbits = nullptr, int64_t* row_kept = nullptr);
+                                            const uint32_t* keepbits = nullptr, int64_t* row_kept = nullptr,
+                                            int64_t n_kept = 0);
 template <typename T> void sum_row_device(salg_ctx* ctx, const salg_csr* c, T* d_out);
 int64_t global_nrows(salg_ctx* ctx, int64_t local_rows);
 

@@ -93,108 +93,94 @@ void panel_gram(salg_ctx* ctx, const T* P, int64_t m, double* d_out) {
 template void panel_gram<float>(salg_ctx*, const float*, int64_t, double*);
 template void panel_gram<double>(salg_ctx*, const double*, int64_t, double*);
 
-// ---- Cholesky G = R^T R of the leading k x k block, R^{-1}; one CTA of 64 threads ---------------------------------
-// Right-looking Cholesky: thread i keeps row i of the trailing matrix in REGISTERS; the column loop is a runtime
-// loop (small code: straight-line unrolling of all 64 columns was instruction-fetch bound), the 64-wide trailing
-// update inside it is unrolled with static register indices and predicates.  The triangular inverse keeps column
-// c of R^{-1} in registers the same way.  This kernel is replicated on every GPU of a row-sharded run and runs ~20
-// times per fit, so its latency is serial time at any GPU count (first version: 90 us per call).
-// Pivots that are not safely positive are floored (rank-deficient panels: l > rank(A)); flag bit 1 is raised, the
-// caller's second CholeskyQR pass re-orthonormalises the affected directions.
+// ---- Cholesky G = L L^T of the leading k x k block, R = L^T and R^{-1}; one CTA of 512 threads ----------------------
+// This kernel is replicated on every GPU of a row-sharded run and runs ~25 times per fit, so its latency is serial
+// time at any GPU count (the first version, one thread per row with the row in registers, took 92 us per call).
+// Here the matrix lives in shared memory and every elimination step is ONE block-wide rank-1 update behind ONE
+// barrier: step j updates the trailing block of A (columns > j) and, in the same sweep, the forward substitution of
+// the identity (columns <= j of B), so L^{-1} falls out of the same 64 steps.  Column j of A is left UNSCALED
+// (readers multiply by 1/l_jj), which is what removes the second barrier of the textbook loop.
+// Thread (g, c): column c, rows g, g + 8, ..., g + 56.  Pivots that are not safely positive are floored
+// (rank-deficient panels: l > rank(A)); flag bit 1 is raised, the caller's second CholeskyQR pass re-orthonormalises.
+constexpr int CHOL_THREADS = 512;
+constexpr int CHOL_LD = LP + 1;
+constexpr size_t CHOL_SMEM = (size_t)(2 * LP * CHOL_LD + 2 * LP + 2) * sizeof(double);
+
 template <typename T>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(CHOL_THREADS)
 chol_inv_kernel(const double* __restrict__ G, int k, double* __restrict__ R, double* __restrict__ Rinv,
                 T* __restrict__ RinvT, int* __restrict__ flag) {
-    __shared__ double Ls[LP][LP + 1];     // L (lower), identity outside the leading k x k block
-    __shared__ double col[LP];            // current column of L, broadcast to every thread
-    __shared__ double dinv[LP];           // 1 / L[j][j]
-    __shared__ double s_md[2], s_dinv;
-    const int i = threadIdx.x;            // this thread owns row i of L and column i of R^{-1}
-    double row[LP];
+    extern __shared__ double chol_sm[];
+    double* A = chol_sm;                       // [64][65] lower triangle: trailing matrix, later unscaled columns of L
+    double* B = A + LP * CHOL_LD;              // [64][65] forward-substituted identity, later unscaled rows of L^{-1}
+    double* dinv = B + LP * CHOL_LD;           // 1 / l_jj
+    double* ldiag = dinv + LP;                 // l_jj
+    double* s_md = ldiag + LP;                 // [2]
+    const int tid = threadIdx.x;
+    const int c = tid & 63, g = tid >> 6;
 #pragma unroll
-    for (int c = 0; c < LP; c++) row[c] = (i < k && c < k && c <= i) ? G[i * LP + c] : 0.0;
-    {
-        double md = 0.0;
-#pragma unroll
-        for (int c = 0; c < LP; c++) if (c == i) md = row[c];
+    for (int m = 0; m < 8; m++) {
+        const int t = g + 8 * m;
+        A[t * CHOL_LD + c] = (t < k && c < k) ? ((c <= t) ? G[t * LP + c] : 0.0) : ((t == c) ? 1.0 : 0.0);
+        B[t * CHOL_LD + c] = (t == c) ? 1.0 : 0.0;
+    }
+    if (tid < 64) {
+        double md = (tid < k) ? G[tid * LP + tid] : 0.0;
 #pragma unroll
         for (int o = 16; o; o >>= 1) md = fmax(md, __shfl_xor_sync(0xFFFFFFFFu, md, o));
-        if ((i & 31) == 0) s_md[i >> 5] = md;
+        if ((tid & 31) == 0) s_md[tid >> 5] = md;
     }
     __syncthreads();
     const double mdiag = fmax(s_md[0], s_md[1]);
     const double floor_piv = (mdiag > 0.0 ? mdiag : 1.0) * 1e-13;
     bool bad = false;
-    double cur = row[0];                  // row[j] of the column about to be processed (carried, no 64-way select)
     for (int j = 0; j < k; j++) {
-        if (i == j) {
-            double p = cur;
-            if (!(p > floor_piv)) {
-                p = floor_piv;
-                bad = true;
+        double p = A[j * CHOL_LD + j];
+        if (!(p > floor_piv)) {
+            p = floor_piv;
+            bad = true;
+        }
+        const double di = rsqrt(p);
+        if (tid == 0) {
+            dinv[j] = di;
+            ldiag[j] = p * di;
+        }
+        // the row-j factors this thread needs: l_cj (trailing update) or (L^{-1})_jc (substitution), both scaled once
+        const double rowj = ((c > j) ? A[c * CHOL_LD + j] : B[j * CHOL_LD + c]) * di;
+        double* M = (c > j) ? A : B;
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            const int t = g + 8 * m;
+            if (t > j && (c <= j || c <= t)) {
+                const double ltj = A[t * CHOL_LD + j] * di;
+                M[t * CHOL_LD + c] = fma(-ltj, rowj, M[t * CHOL_LD + c]);
             }
-            cur = p;
-            s_dinv = rsqrt(p);            // the pivot chain is the serial part: reciprocal square root, no divide
         }
         __syncthreads();
-        const double di = s_dinv;
-        const double lij = (i == j) ? cur * di : ((i > j && i < k) ? cur * di : 0.0);
-        col[i] = lij;                     // (all threads left the previous update loop before the barrier above)
-        Ls[i][j] = lij;
-        if (i == j) dinv[j] = di;
-        __syncthreads();
-        // trailing update: row[c] -= L[i][j] * L[c][j] for j < c <= i; keep the next column's entry at hand
-        double nxt = 0.0;
-#pragma unroll
-        for (int c = 0; c < LP; c++) {
-            const double lcj = col[c];
-            if (c > j && c <= i) row[c] = fma(-lij, lcj, row[c]);
-            if (c == j + 1) nxt = row[c];
-        }
-        cur = nxt;
     }
-    if (bad) atomicOr(flag, 1);
-    // identity outside the leading block (rows >= k entirely; columns >= k of rows < k)
-#pragma unroll 1
-    for (int c = 0; c < LP; c++) {
-        if (i >= k) Ls[i][c] = (c == i) ? 1.0 : 0.0;
-        else if (c >= k) Ls[i][c] = 0.0;
+    if (bad && tid == 0) atomicOr(flag, 1);
+    if (tid < 64 && tid >= k) {
+        dinv[tid] = 1.0;
+        ldiag[tid] = 1.0;
     }
-    if (i >= k) dinv[i] = 1.0;
     __syncthreads();
-    // R = L^T (upper).  Column i of X = R^{-1}: X[r][i] = (delta_ri - sum_{t>r} R[r][t] X[t][i]) / R[r][r],
-    // R[r][t] = L[t][r] broadcast from shared memory, X[.][i] in registers (zero below the diagonal: t > i).
-    double x[LP];
+    // outputs (row-major 64 x 64): R[r][i] = L[i][r], Rinv[r][i] = (L^{-1})[i][r]; thread (g, c) writes rows r = g + 8m,
+    // column i = c (consecutive threads -> consecutive addresses)
 #pragma unroll
-    for (int r = 0; r < LP; r++) x[r] = 0.0;
-    for (int r = LP - 1; r >= 0; r--) {
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-#pragma unroll
-        for (int t = 0; t < LP; t += 4) {
-            a0 = fma(Ls[t][r], x[t], a0);
-            a1 = fma(Ls[t + 1][r], x[t + 1], a1);
-            a2 = fma(Ls[t + 2][r], x[t + 2], a2);
-            a3 = fma(Ls[t + 3][r], x[t + 3], a3);
-        }
-        // x[t] is still 0 for every t <= r at this point (filled from the bottom up), so the sum covers t > r only
-        const double num = ((r == i) ? 1.0 : 0.0) - ((a0 + a1) + (a2 + a3));
-        const double xr = (r <= i) ? num * dinv[r] : 0.0;
-#pragma unroll
-        for (int t = 0; t < LP; t++) if (t == r) x[t] = xr;
-    }
-    // outputs: thread i writes column i of Rinv / RinvT / R (consecutive threads -> consecutive addresses)
-#pragma unroll
-    for (int r = 0; r < LP; r++) {
-        if (Rinv) Rinv[r * LP + i] = x[r];
-        if (RinvT) RinvT[r * LP + i] = (T)x[r];
-        if (R) R[r * LP + i] = (r <= i) ? Ls[i][r] : 0.0;
+    for (int m = 0; m < 8; m++) {
+        const int r = g + 8 * m, i = c;
+        const double x = (r <= i) ? B[i * CHOL_LD + r] * dinv[i] : 0.0;
+        if (Rinv) Rinv[r * LP + i] = x;
+        if (RinvT) RinvT[r * LP + i] = (T)x;
+        if (R) R[r * LP + i] = (r < i) ? A[i * CHOL_LD + r] * dinv[r] : ((r == i) ? ldiag[r] : 0.0);
     }
 }
 
 template <typename T>
 void chol_inv(salg_ctx* ctx, const double* d_G, int k, double* d_R, double* d_Rinv, T* d_RinvT, int* d_flag) {
     ProfScope ps(ctx, PROF_CHOL, 0.0);
-    chol_inv_kernel<T><<<1, 64, 0, ctx->stream>>>(d_G, k, d_R, d_Rinv, d_RinvT, d_flag);
+    SALG_CUDA(cudaFuncSetAttribute(chol_inv_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHOL_SMEM));
+    chol_inv_kernel<T><<<1, CHOL_THREADS, CHOL_SMEM, ctx->stream>>>(d_G, k, d_R, d_Rinv, d_RinvT, d_flag);
     ctx->n_launch++;
     SALG_CUDA(cudaGetLastError());
 }

@@ -112,13 +112,19 @@ static salg_pca* pca_fit(salg_ctx* ctx, const salg_csr* x, const salg_pca_params
         DevBuf<int64_t> d_row_kept;
         if (mask) {
             // the compaction's count pass rides on the statistics pass (one read of the CSR instead of two)
-            std::vector<uint32_t> bits((size_t)(ncols + 31) / 32, 0u);
+            const size_t nw32 = (size_t)(ncols + 31) / 32;
+            std::vector<uint32_t> bits(2 * nw32, 0u);     // mask words, then their exclusive prefix popcounts
             for (int64_t c = 0; c < ncols; c++)
                 if (mask[c]) bits[c >> 5] |= 1u << (c & 31);
+            uint32_t run = 0;
+            for (size_t w = 0; w < nw32; w++) {
+                bits[nw32 + w] = run;
+                run += (uint32_t)__builtin_popcount(bits[w]);
+            }
             DevBuf<uint32_t> d_bits(bits.size(), st);
             SALG_CUDA(cudaMemcpyAsync(d_bits.get(), bits.data(), bits.size() * 4, cudaMemcpyHostToDevice, st));
             d_row_kept.alloc((size_t)x->nrows + 1, st);
-            col_stats_device<T>(ctx, x, d_sum.get(), d_sq.get(), nullptr, d_bits.get(), d_row_kept.get());
+            col_stats_device<T>(ctx, x, d_sum.get(), d_sq.get(), nullptr, d_bits.get(), d_row_kept.get(), (int64_t)run);
             SALG_CUDA(cudaStreamSynchronize(st));
         } else {
             col_stats_device<T>(ctx, x, d_sum.get(), d_sq.get(), nullptr);

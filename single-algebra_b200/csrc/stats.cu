@@ -159,16 +159,92 @@ col_stats_tiled_kernel(const int64_t* __restrict__ ptr, const uint32_t* __restri
     }
 }
 
+// ---- variant 3 (masked fits): one shared-memory tile for the whole column range --------------------------------
+// A masked fit needs the sum of every column (mean_ has full length, pca/sparse_masked/mod.rs:280-291) but the sum of
+// squares only of the kept ones (total_var, :303-307): sum[ncols] + sumsq[n_kept] fit one tile where sum + sumsq of
+// every column would need two (and with them a binary search per row and tile).  Warp per row, 8 independent
+// 128 B loads per array in flight per warp; the kept-entry count of the row (the compaction's count pass) rides along.
+// kb = keep bitmask words followed by the exclusive prefix popcounts of the words (rank of a kept column).
+template <typename T>
+__global__ void __launch_bounds__(1024, 1)
+col_stats_masked_kernel(const int64_t* __restrict__ ptr, const uint32_t* __restrict__ col, const T* __restrict__ val,
+                        int64_t nrows, int ncols, int n_kept, double* __restrict__ g_sum, double* __restrict__ g_sumsq,
+                        const uint32_t* __restrict__ keepbits, unsigned long long* __restrict__ row_kept) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nw32 = (ncols + 31) / 32;
+    float* sum = reinterpret_cast<float*>(smem_raw);          // [ncols]
+    float* sq = sum + ncols;                                   // [n_kept]
+    unsigned* kb = reinterpret_cast<unsigned*>(sq + n_kept);   // [nw32] bits, [nw32] prefix
+    const unsigned* kpre = kb + nw32;
+    for (int i = threadIdx.x; i < ncols + n_kept; i += blockDim.x) sum[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * nw32; i += blockDim.x) kb[i] = keepbits[i];
+    __syncthreads();
+    const int64_t per = (nrows + gridDim.x - 1) / gridDim.x;
+    const int64_t r0 = (int64_t)blockIdx.x * per, r1 = r0 + per < nrows ? r0 + per : nrows;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    constexpr int U = 8;
+    for (int64_t r = r0 + warp; r < r1; r += nwarp) {
+        const int64_t s = ptr[r], e = ptr[r + 1];
+        int kept = 0;
+        for (int64_t p = s + lane; p < e; p += 32 * U) {
+            uint32_t cc[U];
+            T vv[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int64_t q = p + 32 * u;
+                const bool ok = q < e;
+                cc[u] = ok ? __ldcs(col + q) : 0xFFFFFFFFu;
+                vv[u] = ok ? __ldcs(val + q) : T(0);
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                if (cc[u] != 0xFFFFFFFFu) {
+                    const float x = (float)vv[u];
+                    atomicAdd(&sum[cc[u]], x);
+                    const unsigned w = cc[u] >> 5, b = cc[u] & 31u;
+                    const unsigned word = kb[w];
+                    if ((word >> b) & 1u) {
+                        kept++;
+                        atomicAdd(&sq[kpre[w] + __popc(word & ((1u << b) - 1u))], x * x);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) kept += __shfl_xor_sync(0xFFFFFFFFu, kept, o);
+        if (lane == 0) row_kept[r] = (unsigned long long)kept;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < ncols; i += blockDim.x) {
+        const float sv = sum[i];
+        if (sv != 0.f) atomicAdd(&g_sum[i], (double)sv);
+        const unsigned w = (unsigned)i >> 5, b = (unsigned)i & 31u;
+        const unsigned word = kb[w];
+        if (g_sumsq && ((word >> b) & 1u)) {
+            const float q = sq[kpre[w] + __popc(word & ((1u << b) - 1u))];
+            if (q != 0.f) atomicAdd(&g_sumsq[i], (double)q);
+        }
+    }
+}
+
 template <typename T, typename A, bool CNT>
 static void col_stats_launch(salg_ctx* ctx, const salg_csr* c, double* d_sum, double* d_sumsq, double* d_cnt,
-                             const uint32_t* keepbits, int64_t* row_kept) {
+                             const uint32_t* keepbits, int64_t* row_kept, int64_t n_kept) {
     cudaStream_t st = ctx->stream;
     const size_t kMaxSmem = 200 * 1024;
     size_t per_col = 2 * sizeof(A) + (CNT ? 4 : 0);
     int ncols = (int)c->ncols;
     size_t kb_bytes = keepbits ? (size_t)((ncols + 31) / 32) * 4 : 0;
     size_t need = per_col * (size_t)ncols;
-    if (need <= kMaxSmem && !keepbits) {
+    const size_t need_masked = ((size_t)ncols + (size_t)n_kept) * 4 + 2 * kb_bytes;
+    if (keepbits && row_kept && !CNT && sizeof(T) == 4 && need_masked <= kMaxSmem && !getenv("SALG_STATS_TILED")) {
+        auto k = col_stats_masked_kernel<T>;
+        SALG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+        int grid = (int)(c->nrows < ctx->sm_count ? (c->nrows > 0 ? c->nrows : 1) : ctx->sm_count);
+        k<<<grid, 1024, need_masked, st>>>(c->row_ptr, c->col, (const T*)c->val, c->nrows, ncols, (int)n_kept, d_sum, d_sumsq,
+                                           keepbits, (unsigned long long*)row_kept);
+        ctx->n_launch++;
+    } else if (need <= kMaxSmem && !keepbits) {
         auto k = col_stats_flat_kernel<T, A, CNT>;
         SALG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
         int64_t n4 = (c->nnz + 3) / 4;
@@ -195,7 +271,7 @@ static void col_stats_launch(salg_ctx* ctx, const salg_csr* c, double* d_sum, do
 
 template <typename T>
 void col_stats_device(salg_ctx* ctx, const salg_csr* c, double* d_sum, double* d_sumsq, double* d_cnt,
-                      const uint32_t* keepbits, int64_t* row_kept) {
+                      const uint32_t* keepbits, int64_t* row_kept, int64_t n_kept) {
     cudaStream_t st = ctx->stream;
     int64_t ncols = c->ncols;
     if (ncols == 0) return;
@@ -208,11 +284,11 @@ void col_stats_device(salg_ctx* ctx, const salg_csr* c, double* d_sum, double* d
         // f32 matrices accumulate per-CTA partials in f32 (exact for integer counts below 2^24 per CTA
         // chunk), f64 matrices in f64; the cross-CTA reduction is always f64.
         if (sizeof(T) == 4) {
-            if (d_cnt) col_stats_launch<T, float, true>(ctx, c, d_sum, d_sumsq, d_cnt, keepbits, row_kept);
-            else col_stats_launch<T, float, false>(ctx, c, d_sum, d_sumsq, d_cnt, keepbits, row_kept);
+            if (d_cnt) col_stats_launch<T, float, true>(ctx, c, d_sum, d_sumsq, d_cnt, keepbits, row_kept, n_kept);
+            else col_stats_launch<T, float, false>(ctx, c, d_sum, d_sumsq, d_cnt, keepbits, row_kept, n_kept);
         } else {
-            if (d_cnt) col_stats_launch<T, double, true>(ctx, c, d_sum, d_sumsq, d_cnt, keepbits, row_kept);
-            else col_stats_launch<T, double, false>(ctx, c, d_sum, d_sumsq, d_cnt, keepbits, row_kept);
+            if (d_cnt) col_stats_launch<T, double, true>(ctx, c, d_sum, d_sumsq, d_cnt, keepbits, row_kept, n_kept);
+            else col_stats_launch<T, double, false>(ctx, c, d_sum, d_sumsq, d_cnt, keepbits, row_kept, n_kept);
         }
     }
     // row-sharded context: global column sums
@@ -220,8 +296,8 @@ void col_stats_device(salg_ctx* ctx, const salg_csr* c, double* d_sum, double* d
     if (d_sumsq) allreduce_f64(ctx, d_sumsq, (size_t)ncols);
     if (d_cnt) allreduce_f64(ctx, d_cnt, (size_t)ncols);
 }
-template void col_stats_device<float>(salg_ctx*, const salg_csr*, double*, double*, double*, const uint32_t*, int64_t*);
-template void col_stats_device<double>(salg_ctx*, const salg_csr*, double*, double*, double*, const uint32_t*, int64_t*);
+template void col_stats_device<float>(salg_ctx*, const salg_csr*, double*, double*, double*, const uint32_t*, int64_t*, int64_t);
+template void col_stats_device<double>(salg_ctx*, const salg_csr*, double*, double*, double*, const uint32_t*, int64_t*, int64_t);
 
 // ---- sum_row ----------------------------------------------------------------------------------------------
 template <typename T>

@@ -223,6 +223,106 @@ __global__ void tc_tile_ptr_kernel(const uint32_t* __restrict__ keys_sorted, int
     tile_ptr[t] = lo;
 }
 
+// One CTA per 128-row block: the block's entries are contiguous in the CSR, so the tile order (row block, column block)
+// is a counting sort INSIDE the block's own range [ptr[128 rb], ptr[128 (rb+1)]) — histogram of column blocks in shared
+// memory, exclusive scan -> tile_ptr, second sweep (L2-resident) places the entries.  The order of the entries inside a
+// tile does not matter (every entry owns its slot of the dense tile), so placement uses warp-aggregated shared-memory
+// cursors instead of a stable global radix sort (measured 4.2 ms -> see profiles/ for the cfg3 operator).
+constexpr int TC_BIN_THREADS = 512;
+constexpr int TC_BIN_MAX_CB = 4096;
+template <typename T>
+__global__ void __launch_bounds__(TC_BIN_THREADS)
+tc_bin_kernel(const int64_t* __restrict__ ptr, const uint32_t* __restrict__ col, const T* __restrict__ val, int64_t nrows,
+              int64_t nnz, int n_rb, int n_cb, uint2* __restrict__ entries, int64_t* __restrict__ tile_ptr,
+              unsigned* __restrict__ info /* [0] inexact flag, [1] bits of max |v| */) {
+    extern __shared__ unsigned bin_sm[];
+    unsigned* hist = bin_sm;             // [n_cb] counts, then running cursors
+    __shared__ unsigned s_warp[TC_BIN_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = TC_BIN_THREADS / 32;
+    for (int rb = blockIdx.x; rb < n_rb; rb += gridDim.x) {
+        const int64_t r0 = (int64_t)rb * TC_RB;
+        const int64_t r1 = r0 + TC_RB < nrows ? r0 + TC_RB : nrows;
+        int64_t* tp = tile_ptr + (int64_t)rb * n_cb;
+        if (r0 >= nrows) {                                    // padding row block: empty tiles at the end of the stream
+            for (int i = tid; i < n_cb; i += TC_BIN_THREADS) tp[i] = nnz;
+            continue;
+        }
+        const int64_t base = ptr[r0];
+        __syncthreads();
+        for (int i = tid; i < n_cb; i += TC_BIN_THREADS) hist[i] = 0;
+        __syncthreads();
+        // sweep 1: column-block histogram (columns ascend inside a row: equal blocks sit in adjacent lanes)
+        for (int64_t r = r0 + warp; r < r1; r += NW) {
+            const int64_t s = ptr[r], e = ptr[r + 1];
+            for (int64_t p0 = s; p0 < e; p0 += 32) {
+                const int64_t p = p0 + lane;
+                const bool ok = p < e;
+                const unsigned cb = ok ? col[p] / TC_CB : 0xFFFFFFFFu;
+                const unsigned peers = __match_any_sync(0xFFFFFFFFu, cb);
+                if (ok && lane == __ffs(peers) - 1) atomicAdd(&hist[cb], (unsigned)__popc(peers));
+            }
+        }
+        __syncthreads();
+        // exclusive scan of the histogram (n_cb <= 4096: each thread owns a contiguous run)
+        const int per = (n_cb + TC_BIN_THREADS - 1) / TC_BIN_THREADS;
+        const int i0 = tid * per, i1 = (i0 + per < n_cb) ? i0 + per : n_cb;
+        unsigned mine = 0;
+        for (int i = i0; i < i1; i++) mine += hist[i];
+        unsigned incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        unsigned woff = 0;
+        for (int w = 0; w < warp; w++) woff += s_warp[w];
+        unsigned run = woff + incl - mine;
+        for (int i = i0; i < i1; i++) {
+            const unsigned cnt = hist[i];
+            hist[i] = run;                                    // cursor of tile (rb, i), relative to `base`
+            tp[i] = base + run;
+            run += cnt;
+        }
+        __syncthreads();
+        // sweep 2: place the entries
+        bool bad = false;
+        float amax = 0.f;
+        const unsigned rb1 = (unsigned)rb & 1u;
+        for (int64_t r = r0 + warp; r < r1; r += NW) {
+            const int64_t s = ptr[r], e = ptr[r + 1];
+            const unsigned lr = (unsigned)(r - r0);
+            for (int64_t p0 = s; p0 < e; p0 += 32) {
+                const int64_t p = p0 + lane;
+                const bool ok = p < e;
+                const unsigned c = ok ? col[p] : 0u;
+                const unsigned cb = ok ? c / TC_CB : 0xFFFFFFFFu;
+                const unsigned peers = __match_any_sync(0xFFFFFFFFu, cb);
+                const int leader = __ffs(peers) - 1;
+                unsigned start = 0;
+                if (ok && lane == leader) start = atomicAdd(&hist[cb], (unsigned)__popc(peers));
+                start = __shfl_sync(0xFFFFFFFFu, start, leader);
+                if (ok) {
+                    const float v = (float)val[p];
+                    const unsigned lc = c % TC_CB;
+                    // positions inside the 32 KB sparse-operand buffers of the two kernels (see tc_scatter_role)
+                    const uint32_t off_ax = canon_off(lr + 128u * rb1, lc, 4096u) >> 1;
+                    const uint32_t off_aty = canon_off(lc + 64u * (cb & 1u), lr, 2048u) >> 1;
+                    entries[base + start + __popc(peers & ((1u << lane) - 1u))] =
+                        make_uint2(off_ax | (off_aty << 14), __float_as_uint(v));
+                    bad |= (__half2float(__float2half_rn(v)) != v);
+                    amax = fmaxf(amax, fabsf(v));
+                }
+            }
+        }
+        if (bad) atomicOr(&info[0], 1u);
+        atomicMax(&info[1], __float_as_uint(amax));
+    }
+    if (blockIdx.x == 0 && tid == 0) tile_ptr[(int64_t)n_rb * n_cb] = nnz;
+}
+
 template <typename T>
 void* tc_build(salg_ctx* ctx, const salg_csr* c) {
     cudaStream_t st = ctx->stream;
@@ -241,8 +341,17 @@ void* tc_build(salg_ctx* ctx, const salg_csr* c) {
         DevBuf<unsigned> info(2, st);
         SALG_CUDA(cudaMemsetAsync(info.get(), 0, 8, st));
         int64_t nnz = c->nnz;
-        DevBuf<uint32_t> keys((size_t)nnz + 1, st), keys_out((size_t)nnz + 1, st);
-        if (nnz) {
+        const bool binned = t->n_cb <= TC_BIN_MAX_CB && !getenv("SALG_TC_SORT_BUILD");
+        if (binned) {
+            const size_t sm = (size_t)t->n_cb * sizeof(unsigned);
+            int grid = t->n_rb < ctx->sm_count * 4 ? t->n_rb : ctx->sm_count * 4;
+            tc_bin_kernel<T><<<grid, TC_BIN_THREADS, sm, st>>>(c->row_ptr, c->col, (const T*)c->val, c->nrows, nnz, t->n_rb,
+                                                              t->n_cb, t->entries, t->tile_ptr, info.get());
+            ctx->n_launch++;
+            SALG_CUDA(cudaGetLastError());
+        }
+        DevBuf<uint32_t> keys(binned ? 0 : (size_t)nnz + 1, st), keys_out(binned ? 0 : (size_t)nnz + 1, st);
+        if (nnz && !binned) {
             DevBuf<uint2> payload((size_t)nnz, st);
             int64_t want = ceil_div(c->nrows * 32, 256);
             int64_t cap = (int64_t)ctx->sm_count * 16;
@@ -261,9 +370,11 @@ void* tc_build(salg_ctx* ctx, const salg_csr* c) {
                                                       (const uint64_t*)payload.get(), (uint64_t*)t->entries, (int)nnz, 0,
                                                       end_bit, st));
         }
-        tc_tile_ptr_kernel<<<(unsigned)ceil_div(n_tiles + 1, 256), 256, 0, st>>>(keys_out.get(), nnz, n_tiles, t->tile_ptr);
-        ctx->n_launch++;
-        SALG_CUDA(cudaGetLastError());
+        if (!binned) {
+            tc_tile_ptr_kernel<<<(unsigned)ceil_div(n_tiles + 1, 256), 256, 0, st>>>(keys_out.get(), nnz, n_tiles, t->tile_ptr);
+            ctx->n_launch++;
+            SALG_CUDA(cudaGetLastError());
+        }
         unsigned h_info[2] = {0, 0};
         SALG_CUDA(cudaMemcpyAsync(h_info, info.get(), 8, cudaMemcpyDeviceToHost, st));
         SALG_CUDA(cudaStreamSynchronize(st));
