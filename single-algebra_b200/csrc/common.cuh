@@ -261,7 +261,12 @@ template <typename T> void spmm_At(salg_ctx* ctx, const salg_csr* c, const T* Y,
 // tile-densified tcgen05 products (f32 operators only).  SALG_SPMM_IMPL=chunk selects the CUDA-core kernels.
 bool tc_enabled(const salg_ctx* ctx);
 void tc_free(salg_ctx* owner, void* tiles);
-void tc_spmm_A(salg_ctx* ctx, const salg_csr* c, const float* X, float* Y, const double* corr);
+void tc_spmm_A(salg_ctx* ctx, const salg_csr* c, const float* X, float* Y, const double* corr, unsigned* d_amax = nullptr);
+size_t tc_yprep_bytes(salg_ctx* ctx, const salg_csr* c);
+void tc_gram_prep(salg_ctx* ctx, const salg_csr* c, const float* Y, const unsigned* d_amax, uint8_t* Yprep, float* d_scales,
+                  double* G /*GRAM_BUF*/);
+void tc_spmm_At_prepped(salg_ctx* ctx, const salg_csr* c, const uint8_t* Yprep, const float* d_scales, float* Z,
+                        const float* mu, const double* corr);
 void tc_spmm_At(salg_ctx* ctx, const salg_csr* c, const float* Y, float* Z, const float* mu, const double* corr);
 
 // ---- dense.cu -------------------------------------------------------------------------------------

@@ -204,10 +204,53 @@ static salg_pca* pca_fit(salg_ctx* ctx, const salg_csr* x, const salg_pca_params
                 ctx->n_launch++;
                 SALG_CUDA(cudaGetLastError());
             }
+            // f32 operators on the tensor-core path: the tall-side normaliser of the intermediate iterations is applied
+            // implicitly.  One fused pass over Y yields its Gram matrix, its column sums and its pre-split fp16 operand;
+            // R^{-1} (Cholesky of the Gram) then multiplies the SMALL side: A_c^T (Y R^{-1}) = (A_c^T Y) R^{-1}.
+            bool fused = false;
+            DevBuf<uint8_t> Yprep;
+            DevBuf<float> yscales;
+            DevBuf<unsigned> yamax;
+            DevBuf<double> Gy;
+            DevBuf<T> RiT;
+            if constexpr (std::is_same<T, float>::value) {
+                fused = tc_enabled(ctx) && tall_norm && q > 0 && !getenv("SALG_NO_FUSED_NORM");
+                if (fused) {
+                    Yprep.alloc(tc_yprep_bytes(ctx, op) + 16, st);
+                    yscales.alloc(2, st);
+                    yamax.alloc(1, st);
+                    Gy.alloc(GRAM_BUF, st);
+                    RiT.alloc(LP * LP, st);
+                }
+            }
+            auto product_A = [&](const T* X) {      // Y = A_c X (corr holds mu^T X)
+                if constexpr (std::is_same<T, float>::value) {
+                    if (fused) {
+                        tc_spmm_A(ctx, op, X, Y.get(), center ? corr.get() : nullptr, yamax.get());
+                        return;
+                    }
+                }
+                spmm_A<T>(ctx, op, X, Y.get(), center ? corr.get() : nullptr, false);
+            };
             // Y = A_c Om
             if (center) panel_colsum<T>(ctx, Om.get(), n_eff, d_mu, corr.get());
-            spmm_A<T>(ctx, op, Om.get(), Y.get(), center ? corr.get() : nullptr, false);
+            product_A(Om.get());
             for (int it = 0; it < q; it++) {
+                if (fused) {
+                    if constexpr (std::is_same<T, float>::value) {
+                        tc_gram_prep(ctx, op, Y.get(), yamax.get(), Yprep.get(), yscales.get(), Gy.get());
+                        allreduce_f64(ctx, Gy.get(), GRAM_BUF);
+                        chol_inv<T>(ctx, Gy.get(), l, nullptr, nullptr, RiT.get(), d_flag.get());
+                        const double* csy = Gy.get() + LP * LP;          // 1^T Y over all ranks' rows
+                        tc_spmm_At_prepped(ctx, op, Yprep.get(), yscales.get(), Z.get(), d_mu, center ? csy : nullptr);
+                        allreduce_panel_T<T>(ctx, Z.get(), (size_t)n_eff * LP, center ? d_mu : nullptr, csy, n_eff);
+                        panel_mul<T>(ctx, Z.get(), n_eff, RiT.get(), Z.get());
+                    }
+                    cholqr2<T>(ctx, Z.get(), n_eff, l, false, nullptr, nullptr, d_flag.get(), 1);
+                    if (center) panel_colsum<T>(ctx, Z.get(), n_eff, d_mu, corr.get());
+                    product_A(Z.get());
+                    continue;
+                }
                 if (tall_norm) {
                     // intermediate iterations only need a well-conditioned basis of span(Y) (the subspace does not
                     // depend on the normaliser): one CholeskyQR pass; the final Q gets two

@@ -32,16 +32,26 @@ namespace salg {
 
 constexpr int TC_RB = 128;          // tile rows
 constexpr int TC_CB = 64;           // tile columns
-constexpr int TC_SCATTER_WARPS = 16;
-constexpr int TC_SCATTER_THREADS = TC_SCATTER_WARPS * 32;
-constexpr int TC_THREADS = (TC_SCATTER_WARPS + 10) * 32;   // + panel loader, mma, 4 epilogue, 4 entry loaders
+// The scatter role is latency-bound (barrier hand-offs, shared-memory round trips, proxy fence), not issue-bound, so
+// it is split into independent GROUPS: group g owns sparse-operand buffer g and builds every TC_GROUPS-th unit while the
+// other groups build theirs and the tensor core consumes an earlier one.
+constexpr int TC_GROUPS = 3;
+constexpr int TC_GROUP_WARPS = 5;
+constexpr int TC_GROUP_THREADS = TC_GROUP_WARPS * 32;
+constexpr int TC_SCATTER_WARPS = TC_GROUPS * TC_GROUP_WARPS;
+constexpr int TC_NS = 5;              // entry-ring slots (one unit = two tiles each)
+constexpr int TC_LOADER_WARPS = TC_NS;  // entry loaders: warp w serves units s = w (mod TC_NS), i.e. ALWAYS slot w — a slot's
+                                        // uses are then ordered by one thread, so its e_free parity wait can never be a
+                                        // whole phase behind (a suspended try_wait parks the whole warp: one lane per warp)
+constexpr int TC_THREADS = (TC_SCATTER_WARPS + 6 + TC_LOADER_WARPS) * 32;   // + panel loader, mma, 4 epilogue, entry loaders
 constexpr int TC_W_BLOAD = TC_SCATTER_WARPS, TC_W_MMA = TC_SCATTER_WARPS + 1, TC_W_EPI = TC_SCATTER_WARPS + 2,
               TC_W_ELOAD = TC_SCATTER_WARPS + 6;
 constexpr int TC_RPAD = 4;            // row blocks are padded to a multiple of this (the A X kernel walks pairs)
 constexpr int TC_SLOT_ENTRIES = 768;  // entries per ring slot (one tile); denser tiles read their tail from global memory
 constexpr int TC_SLOT_BYTES = (TC_SLOT_ENTRIES + 2) * 8;
 constexpr int TC_S_BYTES = 32768;     // sparse operand buffer: 256 x 64 (A X) or 128 x 128 (A^T Y) fp16
-constexpr int TC_NSB = 2;             // sparse operand buffers in flight (scatter runs up to 2 passes ahead of the MMA)
+constexpr int TC_NSB = TC_GROUPS;     // sparse operand buffers: one per scatter group
+constexpr int TC_EPT = (TC_SLOT_ENTRIES + TC_GROUP_THREADS - 1) / TC_GROUP_THREADS;   // ring entries per thread and tile
 constexpr uint32_t TC_SPIN_LIMIT = 1u << 24;
 
 struct TcTiles {
@@ -479,8 +489,6 @@ struct TcSeq {
 };
 
 struct alignas(16) TcSlotMeta { long long e0[2]; int n[2]; int pad[2]; };   // per tile: first entry, entry count, leading pad (0/1)
-constexpr int TC_LOADER_WARPS = 4;   // entry loaders: warp w serves units s = w (mod 4), one lane each (a suspended
-                                     // try_wait parks the whole warp, so lanes of one warp cannot wait independently)
 
 // ---- entry loader role ---------------------------------------------------------------------------------------------------
 template <int NS>
@@ -552,87 +560,77 @@ __device__ __forceinline__ void tc_scatter_one(uint8_t* S, uint2 en, float a_sca
 template <bool ATY, int NS>
 __device__ __forceinline__ void tc_scatter_role(const uint2* __restrict__ entries, int64_t n_units, int a_terms, float a_scale,
                                                 uint8_t* sS, const uint8_t* sRing, const TcSlotMeta* sMeta, uint64_t* e_full,
-                                                uint64_t* e_free, uint64_t* s_full, uint64_t* s_free, uint64_t* d_free, int units_per_d, int nb,
-                                                int tid) {
-    // d_free: the dense-operand stage of a finished group of `units_per_d` units is released here (by warp 0, when it
-    // sees the s_free of the group's last pass) instead of by a second tcgen05.commit of the single MMA thread
+                                                uint64_t* e_free, uint64_t* s_full, uint64_t* s_free, int tid) {
     const int lane = tid & 31;
-    uint32_t pass = 0;
-    int slot = 0;
-    uint32_t slot_use = 0;
-    const uint32_t passes_per_d = (uint32_t)units_per_d * (uint32_t)a_terms;
-    for (int64_t s = 0; s < n_units; s++) {
+    const int grp = (tid >> 5) / TC_GROUP_WARPS;
+    const int gt = tid - grp * TC_GROUP_THREADS;           // thread index inside the group
+    uint8_t* S = sS + grp * TC_S_BYTES;
+    uint32_t lp = 0;                                        // passes this group has built so far
+    for (int64_t s = grp; s < n_units; s += TC_GROUPS) {
+        const int slot = (int)(s % NS);
+        const uint32_t slot_use = (uint32_t)(s / NS);
         const uint2* sl0 = reinterpret_cast<const uint2*>(sRing + (size_t)slot * (2 * TC_SLOT_BYTES));
         const uint2* sl1 = reinterpret_cast<const uint2*>(sRing + (size_t)slot * (2 * TC_SLOT_BYTES) + TC_SLOT_BYTES);
-        for (int term = 0; term < a_terms; term++) {
-            const int sb = pass % TC_NSB;
-            const uint32_t use = pass / TC_NSB;
+        for (int term = 0; term < a_terms; term++, lp++) {
             if (lane == 0) {
-                if (use > 0) {
-                    mbar_wait(&s_free[sb], (use - 1) & 1);
-                    // pass - TC_NSB has retired; if it closed a dense-operand group, hand that stage back to its loader
-                    const uint32_t done = pass - TC_NSB;
-                    if (tid == 0 && d_free && (done + 1) % passes_per_d == 0) mbar_arrive(&d_free[(done / passes_per_d) % nb]);
-                }
+                if (lp > 0) mbar_wait(&s_free[grp], (lp - 1) & 1);     // the MMAs of this buffer's previous pass have retired
                 if (term == 0) mbar_wait(&e_full[slot], slot_use & 1);
             }
             __syncwarp();
-            uint8_t* S = sS + sb * TC_S_BYTES;
-#pragma unroll
-            for (int i = 0; i < TC_S_BYTES / 16 / TC_SCATTER_THREADS; i++)
-                reinterpret_cast<uint4*>(S)[i * TC_SCATTER_THREADS + tid] = make_uint4(0, 0, 0, 0);
+            for (int i = gt; i < TC_S_BYTES / 16; i += TC_GROUP_THREADS) reinterpret_cast<uint4*>(S)[i] = make_uint4(0, 0, 0, 0);
             // this thread's entries of both tiles (independent shared-memory loads, issued before the barrier)
             const int4 mt = *reinterpret_cast<const int4*>(&sMeta[slot].n[0]);     // n0, n1, pad0, pad1
             const int n0 = mt.x, n1 = mt.y;
             constexpr int lim = TC_SLOT_ENTRIES - 1;     // entries guaranteed to sit in the slot whatever the pad
-            const bool ok0 = tid < n0, ok1 = tid + TC_SCATTER_THREADS < n0 && tid + TC_SCATTER_THREADS < lim;
-            const bool ok2 = tid < n1, ok3 = tid + TC_SCATTER_THREADS < n1 && tid + TC_SCATTER_THREADS < lim;
-            uint2 en0 = ok0 ? sl0[mt.z + tid] : make_uint2(0, 0);
-            uint2 en1 = ok1 ? sl0[mt.z + tid + TC_SCATTER_THREADS] : make_uint2(0, 0);
-            uint2 en2 = ok2 ? sl1[mt.w + tid] : make_uint2(0, 0);
-            uint2 en3 = ok3 ? sl1[mt.w + tid + TC_SCATTER_THREADS] : make_uint2(0, 0);
-            named_bar_sync(1, TC_SCATTER_THREADS);       // every thread's clearing stores precede every scatter store
-            if (ok0) tc_scatter_one<ATY>(S, en0, a_scale, term);
-            if (ok1) tc_scatter_one<ATY>(S, en1, a_scale, term);
-            if (ok2) tc_scatter_one<ATY>(S, en2, a_scale, term);
-            if (ok3) tc_scatter_one<ATY>(S, en3, a_scale, term);
+            const int m0 = n0 < lim ? n0 : lim, m1 = n1 < lim ? n1 : lim;
+            uint2 en0[TC_EPT], en1[TC_EPT];
+#pragma unroll
+            for (int k = 0; k < TC_EPT; k++) {
+                const int i = gt + k * TC_GROUP_THREADS;
+                en0[k] = (i < m0) ? sl0[mt.z + i] : make_uint2(0, 0);
+                en1[k] = (i < m1) ? sl1[mt.w + i] : make_uint2(0, 0);
+            }
+            named_bar_sync(1 + grp, TC_GROUP_THREADS);   // every thread's clearing stores precede every scatter store
+#pragma unroll
+            for (int k = 0; k < TC_EPT; k++) {
+                const int i = gt + k * TC_GROUP_THREADS;
+                if (i < m0) tc_scatter_one<ATY>(S, en0[k], a_scale, term);
+                if (i < m1) tc_scatter_one<ATY>(S, en1[k], a_scale, term);
+            }
             if (n0 > lim || n1 > lim) {
-                // rare: a tile with more entries than two per thread / than the slot holds
+                // rare: a tile with more entries than the slot holds reads its tail from global memory
                 for (int k = 0; k < 2; k++) {
                     const int n = k ? n1 : n0;
-                    const uint2* sl = (k ? sl1 : sl0) + (k ? mt.w : mt.z);
                     const long long e0 = sMeta[slot].e0[k];
-                    for (int i = tid + 2 * TC_SCATTER_THREADS; i < n; i += TC_SCATTER_THREADS)
-                        if (i < lim) tc_scatter_one<ATY>(S, sl[i], a_scale, term);
-                    for (int i = lim + tid; i < n; i += TC_SCATTER_THREADS) tc_scatter_one<ATY>(S, entries[e0 + i], a_scale, term);
+                    for (int i = lim + gt; i < n; i += TC_GROUP_THREADS) tc_scatter_one<ATY>(S, entries[e0 + i], a_scale, term);
                 }
             }
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-                mbar_arrive(&s_full[sb]);
+                mbar_arrive(&s_full[grp]);
                 if (term == a_terms - 1) mbar_arrive(&e_free[slot]);   // every lane of this warp has read the slot
             }
-            pass++;
         }
-        if (++slot == NS) { slot = 0; slot_use++; }
     }
 }
 
 // ---- Y = A X - 1 corr^T -----------------------------------------------------------------------------------------------------
 struct AxSmem {
     static constexpr int D_BYTES = 128 * TC_CB * 2;          // 16 KB per stage: panel slice (M = 128) x (K = 64)
-    static constexpr int NB = 4;                             // >= TC_NSB + 2: a stage is released TC_NSB passes late
-    static constexpr int NS = 8;                             // ring slots (one unit = two tiles each)
-    static constexpr int TOTAL = TC_NSB * TC_S_BYTES + NB * D_BYTES + NS * 2 * TC_SLOT_BYTES + 1024;
+    static constexpr int NB = 4;
+    static constexpr int NS = TC_NS;                         // ring slots
+    static constexpr int TOTAL = TC_NSB * TC_S_BYTES + NB * D_BYTES + NS * 2 * TC_SLOT_BYTES + 128;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_ax_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ tile_ptr, int n_rb, int n_cb, int a_terms,
              float a_scale, int64_t nrows, const uint8_t* __restrict__ Xprep, const float* __restrict__ scales,
-             float* __restrict__ Y, const double* __restrict__ corr, int dbg) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+             float* __restrict__ Y, const double* __restrict__ corr, unsigned* __restrict__ amax_out, int dbg) {
+    // (no integer round trip on this pointer: the compiler must keep seeing the shared address space, or every access
+    // below becomes a generic LD/ST; the no-swizzle operand layouts only need 16 B alignment)
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;
     uint8_t* sS = smem;
     uint8_t* sD = sS + TC_NSB * TC_S_BYTES;
     uint8_t* sRing = sD + AxSmem::NB * AxSmem::D_BYTES;
@@ -646,7 +644,7 @@ tc_ax_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ tile
     const int n_mine = ((int)blockIdx.x < n_pairs) ? (n_pairs - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     if (tid == 0) {
         for (int i = 0; i < TC_NSB; i++) {
-            mbar_init(&s_full[i], TC_SCATTER_WARPS);
+            mbar_init(&s_full[i], TC_GROUP_WARPS);
             mbar_init(&s_free[i], 1);
         }
         for (int i = 0; i < 2; i++) {
@@ -659,7 +657,7 @@ tc_ax_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ tile
         }
         for (int i = 0; i < AxSmem::NS; i++) {
             mbar_init(&e_full[i], 1);
-            mbar_init(&e_free[i], TC_SCATTER_WARPS);
+            mbar_init(&e_free[i], TC_GROUP_WARPS);
         }
         fence_barrier_init();
     }
@@ -672,7 +670,7 @@ tc_ax_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ tile
 
     if (warp < TC_SCATTER_WARPS) {
         tc_scatter_role<false, AxSmem::NS>(entries, seq.n_units(), a_terms, a_scale, sS, sRing, sMeta, e_full, e_free, s_full,
-                                           s_free, nullptr, 1, 1, tid);
+                                           s_free, tid);
     } else if (warp >= TC_W_ELOAD) {
         if (lane == 0) tc_entry_loader<AxSmem::NS>(entries, tile_ptr, seq, sRing, sMeta, e_full, e_free, warp - TC_W_ELOAD);
     } else if (warp == TC_W_BLOAD) {
@@ -695,10 +693,9 @@ tc_ax_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ tile
     } else if (warp == TC_W_MMA) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            uint32_t pass = 0, it = 0;
-            uint64_t s_desc[TC_NSB], d_desc[AxSmem::NB];
-            for (int i = 0; i < TC_NSB; i++) s_desc[i] = umma_desc(smem_u32(sS + i * TC_S_BYTES), 4096, 128);
-            for (int i = 0; i < AxSmem::NB; i++) d_desc[i] = umma_desc(smem_u32(sD + i * AxSmem::D_BYTES), 2048, 128);
+            uint32_t it = 0;
+            // descriptors of buffer i = descriptor of buffer 0 + i * (buffer bytes >> 4) (start-address field, no carry out)
+            const uint64_t s_desc0 = umma_desc(smem_u32(sS), 4096, 128), d_desc0 = umma_desc(smem_u32(sD), 2048, 128);
             constexpr uint32_t idesc = tc_idesc(256);
             long long c_acc = 0, c_d = 0, c_s = 0, c_issue = 0, c_commit = 0, t_prev = clock64(), t_begin = t_prev;
             for (int gi = 0; gi < n_mine; gi++) {
@@ -711,17 +708,18 @@ tc_ax_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ tile
                     const int bb = it % AxSmem::NB;
                     mbar_wait(&d_full[bb], (it / AxSmem::NB) & 1);
                     TC_T(c_d);
+                    const int sb = it % TC_GROUPS;                           // unit `it` was built by scatter group sb
+                    const uint32_t lp0 = (it / TC_GROUPS) * (uint32_t)a_terms;
                     for (int term = 0; term < a_terms; term++) {
-                        const int sb = pass % TC_NSB;
-                        mbar_wait(&s_full[sb], (pass / TC_NSB) & 1);
+                        mbar_wait(&s_full[sb], (lp0 + term) & 1);
                         tc_fence_after();
                         TC_T(c_s);
                         // K = 64: four K-steps; dense operand advances 2 chunks x 2048 B, sparse operand 2 x 4096 B
-                        umma_f16_run4(d_tmem, d_desc[bb], s_desc[sb], idesc, (cb | term) != 0, 256, 512);
+                        umma_f16_run4(d_tmem, d_desc0 + (uint64_t)bb * (AxSmem::D_BYTES >> 4), s_desc0 + (uint64_t)sb * (TC_S_BYTES >> 4), idesc,
+                                      (cb | term) != 0, 256, 512);
                         TC_T(c_issue);
                         umma_commit(&s_free[sb]);
                         TC_T(c_commit);
-                        pass++;
                     }
                     umma_commit(&d_free[bb]);
                 }
@@ -739,6 +737,7 @@ tc_ax_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ tile
         const float inv = scales[1];
         const float cr = corr ? (float)corr[pc] : 0.f;
         long long c_wait = 0, c_work = 0, t_prev = clock64();
+        float amax = 0.f;                       // max |Y| of this thread's outputs (scale of the next pre-split)
         for (int gi = 0; gi < n_mine; gi++) {
             const int as = gi & 1;
             mbar_wait_warp(&acc_full[as], (gi >> 1) & 1, lane);
@@ -754,13 +753,22 @@ tc_ax_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ tile
                     float x = __uint_as_float(v[j]);
                     x += __shfl_xor_sync(0xFFFFFFFFu, x, 1);
                     const int64_t row = row0 + c * 32 + j;
-                    if (!(lane & 1) && row < nrows) Y[row * LP + pc] = x * inv - cr;
+                    if (!(lane & 1) && row < nrows) {
+                        const float y = x * inv - cr;
+                        Y[row * LP + pc] = y;
+                        amax = fmaxf(amax, fabsf(y));
+                    }
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_free[as]);
             TC_T(c_work);
+        }
+        if (amax_out) {
+#pragma unroll
+            for (int o = 16; o; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xFFFFFFFFu, amax, o));
+            if (lane == 0 && amax > 0.f) atomicMax(amax_out, __float_as_uint(amax));
         }
         if (blockIdx.x == 0 && warp == TC_W_EPI && lane == 0) { g_tc_dbg[16] = c_wait; g_tc_dbg[17] = c_work; }
     }
@@ -769,21 +777,219 @@ tc_ax_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ tile
     if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
+// ---- fused Gram + pre-split of a tall panel ---------------------------------------------------------------------------------
+// One pass over Y (m x 64 f32): every 128-row block is fetched by one bulk copy, scaled and split into the canonical
+// fp16 two-term operand (M = 128: m = 2*column + term, K = 128 rows) ONCE — the block is stored to global memory as the
+// dense operand of the following A^T Y product and, from the same shared-memory copy, contracted with itself on the
+// tensor core: D[m][n] += sum_k P[m][k] P[n][k] (M = N = 128, fp16 products exact, f32 accumulation in TMEM).  Every
+// GP_DRAIN row blocks the accumulator is drained into f64 shared-memory sums (G[c][c'] = sum over the four term pairs),
+// so the f32 accumulation never spans more than GP_DRAIN * 128 rows.  Replaces four passes over the panel (Gram, R^{-1}
+// apply, |max|, pre-split) of the explicit CholeskyQR step: the power iteration applies R^{-1} to the SMALL side instead
+// (A^T (Y R^{-1}) = (A^T Y) R^{-1}).  Column sums 1^T Y ride along in f64.
+struct GpSmem {
+    static constexpr int STAGES = 3;
+    static constexpr int STAGE_BYTES = TC_RB * LP * 4;        // 32 KB of f32 rows
+    static constexpr int OPS = 2;
+    static constexpr int OP_BYTES = 128 * TC_RB * 2;          // 32 KB canonical operand
+    static constexpr int G_LD = LP + 1;
+    static constexpr int G_BYTES = LP * G_LD * 8;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + OPS * OP_BYTES + G_BYTES + 128;
+};
+constexpr int GP_CONV_WARPS = 8;
+constexpr int GP_W_EPI = GP_CONV_WARPS, GP_W_LOAD = GP_CONV_WARPS + 4, GP_W_MMA = GP_CONV_WARPS + 5,
+              GP_W_STORE = GP_CONV_WARPS + 6;
+constexpr int GP_THREADS = (GP_CONV_WARPS + 7) * 32;
+constexpr int GP_DRAIN = 8;
+
+__global__ void __launch_bounds__(GP_THREADS, 1)
+tc_gram_prep_kernel(const float* __restrict__ Y, int64_t m, int n_rb, const float* __restrict__ scales,
+                    uint8_t* __restrict__ Yprep, double* __restrict__ G /* GRAM_BUF, pre-zeroed */) {
+    // (no integer round trip on this pointer: the compiler must keep seeing the shared address space, or every access
+    // below becomes a generic LD/ST; the no-swizzle operand layouts only need 16 B alignment)
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;
+    uint8_t* sStage = smem;
+    uint8_t* sOp = sStage + GpSmem::STAGES * GpSmem::STAGE_BYTES;
+    double* sG = reinterpret_cast<double*>(sOp + GpSmem::OPS * GpSmem::OP_BYTES);
+    __shared__ uint64_t st_full[GpSmem::STAGES], st_free[GpSmem::STAGES], op_full[GpSmem::OPS], op_free[GpSmem::OPS],
+        acc_full[2], acc_free[2];
+    __shared__ uint32_t s_tmem;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_mine = ((int)blockIdx.x < n_rb) ? (n_rb - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int n_groups = (n_mine + GP_DRAIN - 1) / GP_DRAIN;
+    if (tid == 0) {
+        for (int i = 0; i < GpSmem::STAGES; i++) {
+            mbar_init(&st_full[i], 1);
+            mbar_init(&st_free[i], GP_CONV_WARPS);
+        }
+        for (int i = 0; i < GpSmem::OPS; i++) {
+            mbar_init(&op_full[i], GP_CONV_WARPS);
+            mbar_init(&op_free[i], 2);              // the MMAs' commit + the bulk store of the block
+        }
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_free[i], 4);
+        }
+        fence_barrier_init();
+    }
+    for (int i = tid; i < LP * GpSmem::G_LD; i += GP_THREADS) sG[i] = 0.0;
+    if (warp == 0) tmem_alloc(&s_tmem, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem;
+
+    if (warp < GP_CONV_WARPS) {
+        // ================= converters: f32 rows -> canonical fp16 two-term operand =================
+        const int mrow = tid & 127;                 // operand row: 2 * column + term
+        const int pc = mrow >> 1, term = mrow & 1;
+        const int half = tid >> 7;                  // K octets [8 half, 8 half + 8)
+        const float s = scales[0];
+        double cs = 0.0;
+        for (int it = 0; it < n_mine; it++) {
+            const int64_t rb = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
+            const int stg = it % GpSmem::STAGES, ob = it % GpSmem::OPS;
+            if (lane == 0) {
+                mbar_wait(&st_full[stg], (it / GpSmem::STAGES) & 1);
+                if (it >= GpSmem::OPS) mbar_wait(&op_free[ob], ((it / GpSmem::OPS) - 1) & 1);
+            }
+            __syncwarp();
+            const float* src = reinterpret_cast<const float*>(sStage + stg * GpSmem::STAGE_BYTES);
+            uint8_t* op = sOp + ob * GpSmem::OP_BYTES;
+            const int64_t rows_left = m - rb * TC_RB;       // rows of this block that exist (the stage's tail is stale)
+            float part = 0.f;
+#pragma unroll 2
+            for (int j = 0; j < 8; j++) {
+                const int o = half * 8 + j;
+                unsigned short h[8];
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++) {
+                    const int k = 8 * o + jj;
+                    const float v = (k < rows_left) ? src[k * LP + pc] : 0.f;
+                    part += v;
+                    h[jj] = f16_term(v * s, term);
+                }
+                uint4 q;
+                q.x = h[0] | ((uint32_t)h[1] << 16);
+                q.y = h[2] | ((uint32_t)h[3] << 16);
+                q.z = h[4] | ((uint32_t)h[5] << 16);
+                q.w = h[6] | ((uint32_t)h[7] << 16);
+                const uint32_t off = (uint32_t)o * 2048u + (uint32_t)mrow * 16u;    // canon_off(mrow, 8 o, 2048)
+                *reinterpret_cast<uint4*>(op + off) = q;
+            }
+            if (term == 0) cs += (double)part;
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&op_full[ob]);
+                mbar_arrive(&st_free[stg]);
+            }
+        }
+        if (term == 0 && cs != 0.0) atomicAdd(&G[LP * LP + pc], cs);
+    } else if (warp == GP_W_LOAD) {
+        if (lane == 0) {
+            for (int it = 0; it < n_mine; it++) {
+                const int64_t rb = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
+                const int stg = it % GpSmem::STAGES;
+                if (it >= GpSmem::STAGES) mbar_wait(&st_free[stg], ((it / GpSmem::STAGES) - 1) & 1);
+                int64_t rows = m - rb * TC_RB;
+                if (rows > TC_RB) rows = TC_RB;
+                const uint32_t bytes = (uint32_t)rows * LP * 4u;
+                mbar_expect_tx(&st_full[stg], bytes);
+                bulk_g2s(sStage + stg * GpSmem::STAGE_BYTES, Y + rb * TC_RB * LP, bytes, &st_full[stg]);
+            }
+        }
+    } else if (warp == GP_W_STORE) {
+        // the finished operand block goes to global memory as ONE 32 KB bulk store (it is the dense operand of the next
+        // A^T Y product); per-thread stores here would sit in front of the converters' proxy fence
+        if (lane == 0) {
+            for (int it = 0; it < n_mine; it++) {
+                const int64_t rb = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
+                const int ob = it % GpSmem::OPS;
+                mbar_wait(&op_full[ob], (it / GpSmem::OPS) & 1);
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(Yprep + (size_t)rb * GpSmem::OP_BYTES),
+                             "r"(smem_u32(sOp + ob * GpSmem::OP_BYTES)), "r"((uint32_t)GpSmem::OP_BYTES)
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                mbar_arrive(&op_free[ob]);
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
+    } else if (warp == GP_W_MMA) {
+        if (lane == 0) {
+            const uint64_t desc0 = umma_desc(smem_u32(sOp), 2048, 128);
+            constexpr uint32_t idesc = tc_idesc(128);
+            for (int it = 0; it < n_mine; it++) {
+                const int ob = it % GpSmem::OPS;
+                const int grp = it / GP_DRAIN, as = grp & 1;
+                if (it % GP_DRAIN == 0 && grp >= 2) mbar_wait(&acc_free[as], ((grp >> 1) - 1) & 1);
+                mbar_wait(&op_full[ob], (it / GpSmem::OPS) & 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)as * 128u;
+                // K = 128 rows: eight K-steps of 16, both operands are the SAME buffer (P P^T)
+                const uint64_t desc = desc0 + (uint64_t)ob * (GpSmem::OP_BYTES >> 4);
+                umma_f16_run4(d_tmem, desc, desc, idesc, (it % GP_DRAIN) != 0, 256, 256);
+                umma_f16_run4(d_tmem, desc + 1024, desc + 1024, idesc, 1, 256, 256);
+                umma_commit(&op_free[ob]);
+                if ((it + 1) % GP_DRAIN == 0 || it + 1 == n_mine) umma_commit(&acc_full[as]);
+            }
+        }
+    } else if (warp >= GP_W_EPI && warp < GP_W_EPI + 4) {
+        // ================= drain: TMEM lane = operand row 2c + t; columns = operand rows 2c' + t' =================
+        const int qd = warp & 3;
+        const int c = (qd * 32 + lane) >> 1;
+        for (int grp = 0; grp < n_groups; grp++) {
+            const int as = grp & 1;
+            mbar_wait_warp(&acc_full[as], (grp >> 1) & 1, lane);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c4 = 0; c4 < 4; c4++) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)as * 128u + c4 * 32, v);
+#pragma unroll
+                for (int jj = 0; jj < 16; jj++) {
+                    float x = __uint_as_float(v[2 * jj]) + __uint_as_float(v[2 * jj + 1]);
+                    x += __shfl_xor_sync(0xFFFFFFFFu, x, 1);
+                    if (!(lane & 1)) sG[c * GpSmem::G_LD + c4 * 16 + jj] += (double)x;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_free[as]);
+        }
+        if (n_mine > 0 && !(lane & 1)) {
+            const double s = (double)scales[0];
+            const double inv_s2 = 1.0 / (s * s);
+            for (int cc = 0; cc < LP; cc++) {
+                const double g = sG[c * GpSmem::G_LD + cc];
+                if (g != 0.0) atomicAdd(&G[c * LP + cc], g * inv_s2);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
 // ---- Z += A^T Y (Z pre-initialised with the centring term) ------------------------------------------------------------------
 struct AtySmem {
     static constexpr int D_BYTES = 128 * TC_RB * 2;          // 32 KB per stage: Y row block (M = 128) x (K = 128 rows)
     static constexpr int NB = 2;
-    static constexpr int NS = 8;                             // ring slots (one unit = two tiles each)
+    static constexpr int NS = TC_NS;                         // ring slots
     static constexpr int G = 8;                               // operator column blocks per CTA: 4 units x 128 TMEM columns
-    static constexpr int TOTAL = TC_NSB * TC_S_BYTES + NB * D_BYTES + NS * 2 * TC_SLOT_BYTES + 1024;
+    static constexpr int TOTAL = TC_NSB * TC_S_BYTES + NB * D_BYTES + NS * 2 * TC_SLOT_BYTES + 128;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_aty_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ tile_ptr, int n_rb, int n_cb, int a_terms,
               float a_scale, int64_t n_eff, const uint8_t* __restrict__ Yprep, const float* __restrict__ scales,
               float* __restrict__ Z, int n_groups, int rb_per_range) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // (no integer round trip on this pointer: the compiler must keep seeing the shared address space, or every access
+    // below becomes a generic LD/ST; the no-swizzle operand layouts only need 16 B alignment)
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;
     uint8_t* sS = smem;
     uint8_t* sD = sS + TC_NSB * TC_S_BYTES;
     uint8_t* sRing = sD + AtySmem::NB * AtySmem::D_BYTES;
@@ -803,7 +1009,7 @@ tc_aty_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ til
 
     if (tid == 0) {
         for (int i = 0; i < TC_NSB; i++) {
-            mbar_init(&s_full[i], TC_SCATTER_WARPS);
+            mbar_init(&s_full[i], TC_GROUP_WARPS);
             mbar_init(&s_free[i], 1);
         }
         for (int i = 0; i < AtySmem::NB; i++) {
@@ -812,7 +1018,7 @@ tc_aty_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ til
         }
         for (int i = 0; i < AtySmem::NS; i++) {
             mbar_init(&e_full[i], 1);
-            mbar_init(&e_free[i], TC_SCATTER_WARPS);
+            mbar_init(&e_free[i], TC_GROUP_WARPS);
         }
         mbar_init(&acc_full, 1);
         fence_barrier_init();
@@ -828,7 +1034,7 @@ tc_aty_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ til
     if (warp < TC_SCATTER_WARPS) {
         if (active)
             tc_scatter_role<true, AtySmem::NS>(entries, seq.n_units(), a_terms, a_scale, sS, sRing, sMeta, e_full, e_free, s_full,
-                                               s_free, nullptr, 1, 1, tid);
+                                               s_free, tid);
     } else if (warp >= TC_W_ELOAD) {
         if (active && lane == 0)
             tc_entry_loader<AtySmem::NS>(entries, tile_ptr, seq, sRing, sMeta, e_full, e_free, warp - TC_W_ELOAD);
@@ -845,25 +1051,25 @@ tc_aty_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ til
         }
     } else if (warp == TC_W_MMA) {
         if (lane == 0 && active) {
-            uint32_t pass = 0, it = 0;
-            uint64_t s_desc[TC_NSB], d_desc[AtySmem::NB];
-            for (int i = 0; i < TC_NSB; i++) s_desc[i] = umma_desc(smem_u32(sS + i * TC_S_BYTES), 2048, 128);
-            for (int i = 0; i < AtySmem::NB; i++) d_desc[i] = umma_desc(smem_u32(sD + i * AtySmem::D_BYTES), 2048, 128);
+            uint32_t it = 0, unit = 0;
+            const uint64_t s_desc0 = umma_desc(smem_u32(sS), 2048, 128), d_desc0 = umma_desc(smem_u32(sD), 2048, 128);
             constexpr uint32_t idesc = tc_idesc(128);
             for (int rb = rb0; rb < rb1; rb++, it++) {
                 const int bb = it % AtySmem::NB;
                 mbar_wait(&d_full[bb], (it / AtySmem::NB) & 1);
-                for (int u = 0; u < n_units; u++) {
+                for (int u = 0; u < n_units; u++, unit++) {
                     const uint32_t d_tmem = tmem_base + (uint32_t)u * 128u;
+                    const int sb = unit % TC_GROUPS;                         // built by scatter group sb
+                    const uint32_t lp0 = (unit / TC_GROUPS) * (uint32_t)a_terms;
                     for (int term = 0; term < a_terms; term++) {
-                        const int sb = pass % TC_NSB;
-                        mbar_wait(&s_full[sb], (pass / TC_NSB) & 1);
+                        mbar_wait(&s_full[sb], (lp0 + term) & 1);
                         tc_fence_after();
                         // K = 128 rows: eight K-steps, both operands advance 2 chunks x 2048 B per step
-                        umma_f16_run4(d_tmem, d_desc[bb], s_desc[sb], idesc, ((rb - rb0) | term) != 0, 256, 256);
-                        umma_f16_run4(d_tmem, d_desc[bb] + 1024, s_desc[sb] + 1024, idesc, 1, 256, 256);
+                        const uint64_t dd = d_desc0 + (uint64_t)bb * (AtySmem::D_BYTES >> 4);
+                        const uint64_t sd = s_desc0 + (uint64_t)sb * (TC_S_BYTES >> 4);
+                        umma_f16_run4(d_tmem, dd, sd, idesc, ((rb - rb0) | term) != 0, 256, 256);
+                        umma_f16_run4(d_tmem, dd + 1024, sd + 1024, idesc, 1, 256, 256);
                         umma_commit(&s_free[sb]);
-                        pass++;
                     }
                 }
                 umma_commit(&d_free[bb]);      // once per row block (amortised over the block's units)
@@ -945,8 +1151,8 @@ static void tc_dbg_print(salg_ctx* ctx, const char* what) {
             h[10], h[11], h[12], h[13], h[14], h[15], h[16], h[17]);
 }
 
-// Y (nrows x 64) = A X - 1 corr^T
-void tc_spmm_A(salg_ctx* ctx, const salg_csr* c, const float* X, float* Y, const double* corr) {
+// Y (nrows x 64) = A X - 1 corr^T; d_amax (optional, device, zeroed here) receives the bits of max |Y|
+void tc_spmm_A(salg_ctx* ctx, const salg_csr* c, const float* X, float* Y, const double* corr, unsigned* d_amax) {
     cudaStream_t st = ctx->stream;
     TcTiles* t = tiles_of(ctx, c);
     if (c->nrows == 0) return;
@@ -956,14 +1162,53 @@ void tc_spmm_A(salg_ctx* ctx, const salg_csr* c, const float* X, float* Y, const
     DevBuf<float> scales(2, st);
     DevBuf<unsigned> amax(1, st);
     tc_prepare_panel<TC_CB>(ctx, X, c->ncols, t->n_cb, t->a_scale, scales.get(), amax.get(), Xprep.get());
+    if (d_amax) SALG_CUDA(cudaMemsetAsync(d_amax, 0, 4, st));
     SALG_CUDA(cudaFuncSetAttribute(tc_ax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AxSmem::TOTAL));
     int n_pairs = t->n_rb / 2;
     int grid = n_pairs < ctx->sm_count ? n_pairs : ctx->sm_count;
     tc_ax_kernel<<<grid, TC_THREADS, AxSmem::TOTAL, st>>>(t->entries, t->tile_ptr, t->n_rb, t->n_cb, t->a_terms, t->a_scale,
-                                                          c->nrows, Xprep.get(), scales.get(), Y, corr, getenv("SALG_TC_DBG") ? atoi(getenv("SALG_TC_DBG")) : 0);
+                                                          c->nrows, Xprep.get(), scales.get(), Y, corr, d_amax,
+                                                          getenv("SALG_TC_DBG") ? atoi(getenv("SALG_TC_DBG")) : 0);
     ctx->n_launch++;
     SALG_CUDA(cudaGetLastError());
     tc_dbg_print(ctx, "ax");
+}
+
+// Fused pass over a tall panel Y (c->nrows x 64): Yprep = canonical two-term fp16 operand of Y (scale from d_amax, the
+// bits of max |Y| written by tc_spmm_A), d_scales = {s, 1 / (s a_scale)}, G (GRAM_BUF f64) = [Y^T Y, 1^T Y] (local rows).
+size_t tc_yprep_bytes(salg_ctx* ctx, const salg_csr* c) { return (size_t)tiles_of(ctx, c)->n_rb * AtySmem::D_BYTES; }
+void tc_gram_prep(salg_ctx* ctx, const salg_csr* c, const float* Y, const unsigned* d_amax, uint8_t* Yprep, float* d_scales,
+                  double* G) {
+    cudaStream_t st = ctx->stream;
+    TcTiles* t = tiles_of(ctx, c);
+    SALG_CUDA(cudaMemsetAsync(G, 0, GRAM_BUF * sizeof(double), st));
+    if (c->nrows == 0) return;
+    ProfScope ps(ctx, PROF_GRAM, (double)c->nrows * 60 * 4);
+    tc_scale_kernel<<<1, 1, 0, st>>>(d_amax, t->a_scale, d_scales);
+    ctx->n_launch++;
+    const int n_rb_real = (int)ceil_div(c->nrows, TC_RB);
+    SALG_CUDA(cudaFuncSetAttribute(tc_gram_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GpSmem::TOTAL));
+    int grid = n_rb_real < ctx->sm_count ? n_rb_real : ctx->sm_count;
+    tc_gram_prep_kernel<<<grid, GP_THREADS, GpSmem::TOTAL, st>>>(Y, c->nrows, n_rb_real, d_scales, Yprep, G);
+    ctx->n_launch++;
+    SALG_CUDA(cudaGetLastError());
+}
+
+static void tc_aty_launch(salg_ctx* ctx, const salg_csr* c, TcTiles* t, const uint8_t* Yprep, const float* scales, float* Z);
+
+// Z (ncols x 64) = A^T Y - mu corr^T   (local rows only), Y given pre-split (tc_gram_prep)
+void tc_spmm_At_prepped(salg_ctx* ctx, const salg_csr* c, const uint8_t* Yprep, const float* d_scales, float* Z,
+                        const float* mu, const double* corr) {
+    cudaStream_t st = ctx->stream;
+    TcTiles* t = tiles_of(ctx, c);
+    if (c->ncols == 0) return;
+    double bytes = (double)c->nnz * 8 + (double)(c->nrows + 1) * 8 + (double)c->ncols * 60 * 4 + (double)c->nrows * 60 * 4;
+    ProfScope ps(ctx, PROF_SPMMT, bytes);   // includes the Z initialisation
+    tc_init_z_kernel<<<(unsigned)ceil_div(c->ncols * LP, 256), 256, 0, st>>>(Z, c->ncols, mu, corr);
+    ctx->n_launch++;
+    SALG_CUDA(cudaGetLastError());
+    if (c->nrows == 0) return;
+    tc_aty_launch(ctx, c, t, Yprep, d_scales, Z);
 }
 
 // Z (ncols x 64) = A^T Y - mu corr^T   (local rows only)
@@ -981,6 +1226,11 @@ void tc_spmm_At(salg_ctx* ctx, const salg_csr* c, const float* Y, float* Z, cons
     DevBuf<float> scales(2, st);
     DevBuf<unsigned> amax(1, st);
     tc_prepare_panel<TC_RB>(ctx, Y, c->nrows, t->n_rb, t->a_scale, scales.get(), amax.get(), Yprep.get());
+    tc_aty_launch(ctx, c, t, Yprep.get(), scales.get(), Z);
+}
+
+static void tc_aty_launch(salg_ctx* ctx, const salg_csr* c, TcTiles* t, const uint8_t* Yprep, const float* scales, float* Z) {
+    cudaStream_t st = ctx->stream;
     int n_groups = (int)ceil_div(t->n_cb, AtySmem::G);
     int n_rb_real = (int)ceil_div(c->nrows, TC_RB);
     int ranges = ctx->sm_count / n_groups;
@@ -990,7 +1240,7 @@ void tc_spmm_At(salg_ctx* ctx, const salg_csr* c, const float* Y, float* Z, cons
     ranges = (int)ceil_div(n_rb_real, rb_per_range);
     SALG_CUDA(cudaFuncSetAttribute(tc_aty_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AtySmem::TOTAL));
     tc_aty_kernel<<<n_groups * ranges, TC_THREADS, AtySmem::TOTAL, st>>>(t->entries, t->tile_ptr, n_rb_real, t->n_cb, t->a_terms,
-                                                                         t->a_scale, c->ncols, Yprep.get(), scales.get(), Z,
+                                                                         t->a_scale, c->ncols, Yprep, scales, Z,
                                                                          n_groups, rb_per_range);
     ctx->n_launch++;
     SALG_CUDA(cudaGetLastError());
