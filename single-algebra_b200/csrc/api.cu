@@ -190,6 +190,7 @@ int salg_ctx_destroy(salg_ctx* c) {
         if (c->timer1) cudaEventDestroy(c->timer1);
         for (int i = 0; i < salg_ctx::N_STAGE; i++) {
             if (c->stage[i]) cudaFreeHost(c->stage[i]);
+            if (i == 0 && c->scratch) cudaFree(c->scratch);
             if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
         }
         if (c->comm) ncclCommDestroy(c->comm);

@@ -122,6 +122,10 @@ struct salg_ctx {
     void* stage[N_STAGE] = {nullptr, nullptr, nullptr};
     cudaEvent_t stage_ev[N_STAGE] = {nullptr, nullptr, nullptr};
     size_t stage_bytes = 0;
+    // grow-only device scratch kept across calls (multi-GB temporaries: the stream-ordered pool re-maps memory for an
+    // allocation of that size on every fit, which was measured to cost more than the kernels using it)
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
 };
 
 struct salg_csr {
@@ -223,6 +227,18 @@ inline void dev_free(salg_ctx* owner, void* p) {
     else cudaFree(p);
 }
 
+inline void* ctx_scratch(salg_ctx* ctx, size_t bytes) {
+    if (bytes > ctx->scratch_bytes) {
+        SALG_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->scratch) cudaFree(ctx->scratch);
+        ctx->scratch = nullptr;
+        ctx->scratch_bytes = 0;
+        SALG_CUDA(cudaMalloc(&ctx->scratch, bytes));
+        ctx->scratch_bytes = bytes;
+    }
+    return ctx->scratch;
+}
+
 // ---- csr.cu ---------------------------------------------------------------------------------------
 salg_csr* csr_alloc(salg_ctx* ctx, int dtype, int64_t nrows, int64_t ncols, int64_t nnz);
 void csr_destroy(salg_csr* c);
@@ -240,7 +256,9 @@ void exclusive_scan_i64(salg_ctx* ctx, const int64_t* in, int64_t* out, int64_t 
 // [nrows+1]: also count, per row, the entries in kept columns (the compaction's count pass fused into the statistics pass)
 template <typename T> void col_stats_device(salg_ctx* ctx, const salg_csr* c, double* d_sum, double* d_sumsq, double* d_cnt,
                                             const uint32_t* keepbits = nullptr, int64_t* row_kept = nullptr,
-                                            int64_t n_kept = 0);
+                                            int64_t n_kept = 0, uint32_t* kept_col = nullptr, void* kept_val = nullptr,
+                                            int kept_shift = 0, int* kept_overflow = nullptr);
+bool col_stats_can_fuse_compaction(const salg_csr* c, int64_t n_kept);
 template <typename T> void sum_row_device(salg_ctx* ctx, const salg_csr* c, T* d_out);
 int64_t global_nrows(salg_ctx* ctx, int64_t local_rows);
 
@@ -261,6 +279,9 @@ template <typename T> void spmm_At(salg_ctx* ctx, const salg_csr* c, const T* Y,
 // tile-densified tcgen05 products (f32 operators only).  SALG_SPMM_IMPL=chunk selects the CUDA-core kernels.
 bool tc_enabled(const salg_ctx* ctx);
 void tc_free(salg_ctx* owner, void* tiles);
+// tile format of the operator whose row r lives at [in_ptr[r] >> in_shift, ... + c->row_ptr[r+1] - c->row_ptr[r]) of col / val
+// (fused compaction: the kept entries sit at the rows' scaled ORIGINAL offsets); attaches it to c
+void tc_attach_tiles_f32(salg_ctx* ctx, salg_csr* c, const int64_t* in_ptr, int in_shift, const uint32_t* col, const float* val);
 void tc_spmm_A(salg_ctx* ctx, const salg_csr* c, const float* X, float* Y, const double* corr, unsigned* d_amax = nullptr);
 size_t tc_yprep_bytes(salg_ctx* ctx, const salg_csr* c);
 void tc_gram_prep(salg_ctx* ctx, const salg_csr* c, const float* Y, const unsigned* d_amax, uint8_t* Yprep, float* d_scales,

@@ -110,6 +110,10 @@ static salg_pca* pca_fit(salg_ctx* ctx, const salg_csr* x, const salg_pca_params
         //      pca/sparse_masked/mod.rs:275-311) — one pass instead of the reference's three
         DevBuf<double> d_sum((size_t)ncols, st), d_sq((size_t)ncols, st);
         DevBuf<int64_t> d_row_kept;
+        uint32_t* kept_col = nullptr;     // context scratch (fused compaction)
+        T* kept_val = nullptr;
+        int kept_shift = 0;
+        bool fused_compact = false;
         if (mask) {
             // the compaction's count pass rides on the statistics pass (one read of the CSR instead of two)
             const size_t nw32 = (size_t)(ncols + 31) / 32;
@@ -124,7 +128,31 @@ static salg_pca* pca_fit(salg_ctx* ctx, const salg_csr* x, const salg_pca_params
             DevBuf<uint32_t> d_bits(bits.size(), st);
             SALG_CUDA(cudaMemcpyAsync(d_bits.get(), bits.data(), bits.size() * 4, cudaMemcpyHostToDevice, st));
             d_row_kept.alloc((size_t)x->nrows + 1, st);
-            col_stats_device<T>(ctx, x, d_sum.get(), d_sq.get(), nullptr, d_bits.get(), d_row_kept.get(), (int64_t)run);
+            // f32 randomized fits on the tensor-core path only ever touch the operator through its tile format: the
+            // statistics pass then also WRITES the kept entries (at their rows' original offsets in a scratch of the
+            // operator's size) and the tile builder reads them from there — no second sweep over the full matrix
+            if constexpr (std::is_same<T, float>::value) {
+                fused_compact = tc_enabled(ctx) && prm->svd_method == SALG_SVD_RANDOM && x->nnz > 0 &&
+                                col_stats_can_fuse_compaction(x, (int64_t)run) && !getenv("SALG_NO_FUSED_COMPACT");
+            }
+            DevBuf<int> d_ovf(1, st);
+            if (fused_compact) {
+                // row r's slot in the scratch starts at ptr[r] >> shift: 2^-shift >= 3 x the kept fraction of the columns
+                kept_shift = 0;
+                while (kept_shift < 6 && 3.0 * (double)run * (double)(2 << kept_shift) <= (double)ncols) kept_shift++;
+                const size_t n_slots = (size_t)(x->nnz >> kept_shift) + 32;
+                kept_col = (uint32_t*)ctx_scratch(ctx, n_slots * (4 + sizeof(T)));
+                kept_val = (T*)(kept_col + n_slots);
+                SALG_CUDA(cudaMemsetAsync(d_ovf.get(), 0, 4, st));
+            }
+            col_stats_device<T>(ctx, x, d_sum.get(), d_sq.get(), nullptr, d_bits.get(), d_row_kept.get(), (int64_t)run,
+                                kept_col, kept_val, kept_shift, d_ovf.get());
+            if (fused_compact) {
+                int h_ovf = 0;
+                SALG_CUDA(cudaMemcpyAsync(&h_ovf, d_ovf.get(), 4, cudaMemcpyDeviceToHost, st));
+                SALG_CUDA(cudaStreamSynchronize(st));
+                if (h_ovf) fused_compact = false;      // some row keeps more than its slot holds: separate compaction pass
+            }
             SALG_CUDA(cudaStreamSynchronize(st));
         } else {
             col_stats_device<T>(ctx, x, d_sum.get(), d_sq.get(), nullptr);
@@ -157,7 +185,28 @@ static salg_pca* pca_fit(salg_ctx* ctx, const salg_csr* x, const salg_pca_params
         // ---- operator: the (column-compacted) matrix
         const salg_csr* op = x;
         DevBuf<uint32_t> d_kept;
-        if (mask) {
+        if (mask && fused_compact) {
+            if constexpr (std::is_same<T, float>::value) {
+                // shell of the compacted operator: compact row offsets + tile format, no col / val arrays
+                ProfScope ps(ctx, PROF_COMPACT, 0.0);
+                compact = new salg_csr();
+                compact->ctx = ctx;
+                compact->dtype = x->dtype;
+                compact->nrows = x->nrows;
+                compact->ncols = n_eff;
+                compact->row_ptr = (int64_t*)dev_alloc(ctx, (size_t)(x->nrows + 1) * 8);
+                exclusive_scan_i64(ctx, d_row_kept.get(), compact->row_ptr, x->nrows + 1);
+                int64_t nnz_eff = 0;
+                SALG_CUDA(cudaMemcpyAsync(&nnz_eff, compact->row_ptr + x->nrows, 8, cudaMemcpyDeviceToHost, st));
+                SALG_CUDA(cudaStreamSynchronize(st));
+                compact->nnz = nnz_eff;
+            }
+            if constexpr (std::is_same<T, float>::value)
+                tc_attach_tiles_f32(ctx, compact, x->row_ptr, kept_shift, kept_col, kept_val);
+            op = compact;
+            d_kept.alloc((size_t)n_eff, st);
+            SALG_CUDA(cudaMemcpyAsync(d_kept.get(), kept.data(), (size_t)n_eff * 4, cudaMemcpyHostToDevice, st));
+        } else if (mask) {
             compact = csr_select_columns<T>(ctx, x, mask, d_row_kept.get());
             op = compact;
             d_kept.alloc((size_t)n_eff, st);

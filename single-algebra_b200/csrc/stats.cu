@@ -169,7 +169,14 @@ template <typename T>
 __global__ void __launch_bounds__(1024, 1)
 col_stats_masked_kernel(const int64_t* __restrict__ ptr, const uint32_t* __restrict__ col, const T* __restrict__ val,
                         int64_t nrows, int ncols, int n_kept, double* __restrict__ g_sum, double* __restrict__ g_sumsq,
-                        const uint32_t* __restrict__ keepbits, unsigned long long* __restrict__ row_kept) {
+                        const uint32_t* __restrict__ keepbits, unsigned long long* __restrict__ row_kept,
+                        uint32_t* __restrict__ kept_col, T* __restrict__ kept_val, int kept_shift,
+                        int* __restrict__ kept_overflow) {
+    // kept_col / kept_val (optional, (nnz >> kept_shift) + 16 long): the kept entries of row r, renumbered to compact
+    // column ids and in their original order, are written from ptr[r] >> kept_shift on — the compaction's WRITE pass
+    // fused in as well; the tile builder (tc.cu) consumes them from there, so the 16.8 GB operator is read once, not
+    // twice.  A row whose kept entries do not fit before the next row's slot raises *kept_overflow (the caller then
+    // falls back to the separate compaction pass).
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nw32 = (ncols + 31) / 32;
     float* sum = reinterpret_cast<float*>(smem_raw);          // [ncols]
@@ -185,8 +192,11 @@ col_stats_masked_kernel(const int64_t* __restrict__ ptr, const uint32_t* __restr
     constexpr int U = 8;
     for (int64_t r = r0 + warp; r < r1; r += nwarp) {
         const int64_t s = ptr[r], e = ptr[r + 1];
-        int kept = 0;
-        for (int64_t p = s + lane; p < e; p += 32 * U) {
+        int kept = 0;                                          // warp-uniform running count of kept entries
+        const int64_t ks = s >> kept_shift;
+        const int cap = (int)((e >> kept_shift) - ks);         // slot of this row in the scaled scratch
+        for (int64_t p0 = s; p0 < e; p0 += 32 * U) {           // warp-uniform trip count (ballots inside)
+            const int64_t p = p0 + lane;
             uint32_t cc[U];
             T vv[U];
 #pragma unroll
@@ -198,21 +208,35 @@ col_stats_masked_kernel(const int64_t* __restrict__ ptr, const uint32_t* __restr
             }
 #pragma unroll
             for (int u = 0; u < U; u++) {
+                bool kbit = false;
+                unsigned rank = 0;
+                float x = 0.f;
                 if (cc[u] != 0xFFFFFFFFu) {
-                    const float x = (float)vv[u];
+                    x = (float)vv[u];
                     atomicAdd(&sum[cc[u]], x);
                     const unsigned w = cc[u] >> 5, b = cc[u] & 31u;
                     const unsigned word = kb[w];
-                    if ((word >> b) & 1u) {
-                        kept++;
-                        atomicAdd(&sq[kpre[w] + __popc(word & ((1u << b) - 1u))], x * x);
+                    kbit = (word >> b) & 1u;
+                    rank = kpre[w] + __popc(word & ((1u << b) - 1u));
+                }
+                const unsigned bal = __ballot_sync(0xFFFFFFFFu, kbit);
+                if (kbit) {
+                    atomicAdd(&sq[rank], x * x);
+                    if (kept_col) {
+                        const int k = kept + __popc(bal & ((1u << lane) - 1u));
+                        if (k < cap) {
+                            kept_col[ks + k] = rank;
+                            kept_val[ks + k] = vv[u];
+                        }
                     }
                 }
+                kept += __popc(bal);
             }
         }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) kept += __shfl_xor_sync(0xFFFFFFFFu, kept, o);
-        if (lane == 0) row_kept[r] = (unsigned long long)kept;
+        if (lane == 0) {
+            row_kept[r] = (unsigned long long)kept;
+            if (kept_col && kept > cap) atomicOr(kept_overflow, 1);
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < ncols; i += blockDim.x) {
@@ -229,7 +253,8 @@ col_stats_masked_kernel(const int64_t* __restrict__ ptr, const uint32_t* __restr
 
 template <typename T, typename A, bool CNT>
 static void col_stats_launch(salg_ctx* ctx, const salg_csr* c, double* d_sum, double* d_sumsq, double* d_cnt,
-                             const uint32_t* keepbits, int64_t* row_kept, int64_t n_kept) {
+                             const uint32_t* keepbits, int64_t* row_kept, int64_t n_kept, uint32_t* kept_col, T* kept_val,
+                             int kept_shift, int* kept_overflow) {
     cudaStream_t st = ctx->stream;
     const size_t kMaxSmem = 200 * 1024;
     size_t per_col = 2 * sizeof(A) + (CNT ? 4 : 0);
@@ -242,8 +267,10 @@ static void col_stats_launch(salg_ctx* ctx, const salg_csr* c, double* d_sum, do
         SALG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
         int grid = (int)(c->nrows < ctx->sm_count ? (c->nrows > 0 ? c->nrows : 1) : ctx->sm_count);
         k<<<grid, 1024, need_masked, st>>>(c->row_ptr, c->col, (const T*)c->val, c->nrows, ncols, (int)n_kept, d_sum, d_sumsq,
-                                           keepbits, (unsigned long long*)row_kept);
+                                           keepbits, (unsigned long long*)row_kept, kept_col, kept_val, kept_shift, kept_overflow);
         ctx->n_launch++;
+    } else if (kept_col) {
+        throw Error(SALG_ERR_UNSUPPORTED, "fused compaction needs the single-tile masked statistics kernel");
     } else if (need <= kMaxSmem && !keepbits) {
         auto k = col_stats_flat_kernel<T, A, CNT>;
         SALG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
@@ -271,7 +298,8 @@ static void col_stats_launch(salg_ctx* ctx, const salg_csr* c, double* d_sum, do
 
 template <typename T>
 void col_stats_device(salg_ctx* ctx, const salg_csr* c, double* d_sum, double* d_sumsq, double* d_cnt,
-                      const uint32_t* keepbits, int64_t* row_kept, int64_t n_kept) {
+                      const uint32_t* keepbits, int64_t* row_kept, int64_t n_kept, uint32_t* kept_col, void* kept_val,
+                      int kept_shift, int* kept_overflow) {
     cudaStream_t st = ctx->stream;
     int64_t ncols = c->ncols;
     if (ncols == 0) return;
@@ -284,11 +312,15 @@ void col_stats_device(salg_ctx* ctx, const salg_csr* c, double* d_sum, double* d
         // f32 matrices accumulate per-CTA partials in f32 (exact for integer counts below 2^24 per CTA
         // chunk), f64 matrices in f64; the cross-CTA reduction is always f64.
         if (sizeof(T) == 4) {
-            if (d_cnt) col_stats_launch<T, float, true>(ctx, c, d_sum, d_sumsq, d_cnt, keepbits, row_kept, n_kept);
-            else col_stats_launch<T, float, false>(ctx, c, d_sum, d_sumsq, d_cnt, keepbits, row_kept, n_kept);
+            if (d_cnt) col_stats_launch<T, float, true>(ctx, c, d_sum, d_sumsq, d_cnt, keepbits, row_kept, n_kept, kept_col, (T*)kept_val,
+                                                            kept_shift, kept_overflow);
+            else col_stats_launch<T, float, false>(ctx, c, d_sum, d_sumsq, d_cnt, keepbits, row_kept, n_kept, kept_col, (T*)kept_val,
+                                                            kept_shift, kept_overflow);
         } else {
-            if (d_cnt) col_stats_launch<T, double, true>(ctx, c, d_sum, d_sumsq, d_cnt, keepbits, row_kept, n_kept);
-            else col_stats_launch<T, double, false>(ctx, c, d_sum, d_sumsq, d_cnt, keepbits, row_kept, n_kept);
+            if (d_cnt) col_stats_launch<T, double, true>(ctx, c, d_sum, d_sumsq, d_cnt, keepbits, row_kept, n_kept, kept_col, (T*)kept_val,
+                                                            kept_shift, kept_overflow);
+            else col_stats_launch<T, double, false>(ctx, c, d_sum, d_sumsq, d_cnt, keepbits, row_kept, n_kept, kept_col, (T*)kept_val,
+                                                            kept_shift, kept_overflow);
         }
     }
     // row-sharded context: global column sums
@@ -296,8 +328,15 @@ void col_stats_device(salg_ctx* ctx, const salg_csr* c, double* d_sum, double* d
     if (d_sumsq) allreduce_f64(ctx, d_sumsq, (size_t)ncols);
     if (d_cnt) allreduce_f64(ctx, d_cnt, (size_t)ncols);
 }
-template void col_stats_device<float>(salg_ctx*, const salg_csr*, double*, double*, double*, const uint32_t*, int64_t*, int64_t);
-template void col_stats_device<double>(salg_ctx*, const salg_csr*, double*, double*, double*, const uint32_t*, int64_t*, int64_t);
+template void col_stats_device<float>(salg_ctx*, const salg_csr*, double*, double*, double*, const uint32_t*, int64_t*, int64_t,
+                                      uint32_t*, void*, int, int*);
+template void col_stats_device<double>(salg_ctx*, const salg_csr*, double*, double*, double*, const uint32_t*, int64_t*, int64_t,
+                                       uint32_t*, void*, int, int*);
+// can col_stats_device write the kept entries (kept_col / kept_val) for this matrix / mask?
+bool col_stats_can_fuse_compaction(const salg_csr* c, int64_t n_kept) {
+    const size_t kb = (size_t)((c->ncols + 31) / 32) * 4;
+    return c->dtype == SALG_F32 && ((size_t)c->ncols + (size_t)n_kept) * 4 + 2 * kb <= 200 * 1024 && !getenv("SALG_STATS_TILED");
+}
 
 // ---- sum_row ----------------------------------------------------------------------------------------------
 template <typename T>

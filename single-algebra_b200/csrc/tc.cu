@@ -242,7 +242,8 @@ constexpr int TC_BIN_THREADS = 512;
 constexpr int TC_BIN_MAX_CB = 4096;
 template <typename T>
 __global__ void __launch_bounds__(TC_BIN_THREADS)
-tc_bin_kernel(const int64_t* __restrict__ ptr, const uint32_t* __restrict__ col, const T* __restrict__ val, int64_t nrows,
+tc_bin_kernel(const int64_t* __restrict__ in_ptr, int in_shift, const int64_t* __restrict__ ptr, const uint32_t* __restrict__ col,
+              const T* __restrict__ val, int64_t nrows,
               int64_t nnz, int n_rb, int n_cb, uint2* __restrict__ entries, int64_t* __restrict__ tile_ptr,
               unsigned* __restrict__ info /* [0] inexact flag, [1] bits of max |v| */) {
     extern __shared__ unsigned bin_sm[];
@@ -264,7 +265,7 @@ tc_bin_kernel(const int64_t* __restrict__ ptr, const uint32_t* __restrict__ col,
         __syncthreads();
         // sweep 1: column-block histogram (columns ascend inside a row: equal blocks sit in adjacent lanes)
         for (int64_t r = r0 + warp; r < r1; r += NW) {
-            const int64_t s = ptr[r], e = ptr[r + 1];
+            const int64_t s = in_ptr[r] >> in_shift, e = s + (ptr[r + 1] - ptr[r]);
             for (int64_t p0 = s; p0 < e; p0 += 32) {
                 const int64_t p = p0 + lane;
                 const bool ok = p < e;
@@ -302,7 +303,7 @@ tc_bin_kernel(const int64_t* __restrict__ ptr, const uint32_t* __restrict__ col,
         float amax = 0.f;
         const unsigned rb1 = (unsigned)rb & 1u;
         for (int64_t r = r0 + warp; r < r1; r += NW) {
-            const int64_t s = ptr[r], e = ptr[r + 1];
+            const int64_t s = in_ptr[r] >> in_shift, e = s + (ptr[r + 1] - ptr[r]);
             const unsigned lr = (unsigned)(r - r0);
             for (int64_t p0 = s; p0 < e; p0 += 32) {
                 const int64_t p = p0 + lane;
@@ -334,8 +335,14 @@ tc_bin_kernel(const int64_t* __restrict__ ptr, const uint32_t* __restrict__ col,
 }
 
 template <typename T>
-void* tc_build(salg_ctx* ctx, const salg_csr* c) {
+void* tc_build(salg_ctx* ctx, const salg_csr* c, const int64_t* in_ptr = nullptr, const uint32_t* in_col = nullptr,
+               const T* in_val = nullptr, int in_shift = 0) {
     cudaStream_t st = ctx->stream;
+    if (!in_ptr) {
+        in_ptr = c->row_ptr;
+        in_col = c->col;
+        in_val = (const T*)c->val;
+    }
     SALG_REQUIRE(c->nnz < ((int64_t)1 << 31), SALG_ERR_UNSUPPORTED, "tile format supports < 2^31 stored entries per GPU shard");
     TcTiles* t = new TcTiles();
     try {
@@ -351,11 +358,12 @@ void* tc_build(salg_ctx* ctx, const salg_csr* c) {
         DevBuf<unsigned> info(2, st);
         SALG_CUDA(cudaMemsetAsync(info.get(), 0, 8, st));
         int64_t nnz = c->nnz;
-        const bool binned = t->n_cb <= TC_BIN_MAX_CB && !getenv("SALG_TC_SORT_BUILD");
+        const bool binned = in_ptr != c->row_ptr || (t->n_cb <= TC_BIN_MAX_CB && !getenv("SALG_TC_SORT_BUILD"));
+        SALG_REQUIRE(t->n_cb <= TC_BIN_MAX_CB || in_ptr == c->row_ptr, SALG_ERR_UNSUPPORTED, "too many column blocks");
         if (binned) {
             const size_t sm = (size_t)t->n_cb * sizeof(unsigned);
             int grid = t->n_rb < ctx->sm_count * 4 ? t->n_rb : ctx->sm_count * 4;
-            tc_bin_kernel<T><<<grid, TC_BIN_THREADS, sm, st>>>(c->row_ptr, c->col, (const T*)c->val, c->nrows, nnz, t->n_rb,
+            tc_bin_kernel<T><<<grid, TC_BIN_THREADS, sm, st>>>(in_ptr, in_shift, c->row_ptr, in_col, in_val, c->nrows, nnz, t->n_rb,
                                                               t->n_cb, t->entries, t->tile_ptr, info.get());
             ctx->n_launch++;
             SALG_CUDA(cudaGetLastError());
@@ -404,7 +412,12 @@ void* tc_build(salg_ctx* ctx, const salg_csr* c) {
     }
     return t;
 }
-template void* tc_build<float>(salg_ctx*, const salg_csr*);
+template void* tc_build<float>(salg_ctx*, const salg_csr*, const int64_t*, const uint32_t*, const float*, int);
+
+void tc_attach_tiles_f32(salg_ctx* ctx, salg_csr* c, const int64_t* in_ptr, int in_shift, const uint32_t* col, const float* val) {
+    if (c->tc) tc_free(ctx, c->tc);
+    c->tc = tc_build<float>(ctx, c, in_ptr, col, val, in_shift);
+}
 
 // ---- panel pre-split into the canonical dense-operand layout -------------------------------------------------------
 __global__ void tc_absmax_kernel(const float* __restrict__ P, int64_t n_elems, unsigned* __restrict__ out_bits) {
