@@ -247,6 +247,14 @@ int salg_op_cholqr2_f64(salg_ctx* ctx, const double* panel, int64_t m, int64_t k
 int salg_op_small_svd(salg_ctx* ctx, const double* a, int64_t k, double* u, double* s, double* vt);
 /* Repeats one centred SpMM (transposed or not) `iters` times on a device-resident random panel and
  * returns the average device ms — the microbenchmark behind bench.py's roofline object. */
+/* Test / probe hook for the fused tall-panel pass of the f32 tensor-core path (tc.cu: tc_gram_prep_kernel): Gram matrix
+ * (k x k row-major) and column sums of a panel in one pass, f32 products exact in fp16 two-term form, f32 accumulation
+ * drained to f64 every 1024 rows.  It replaces the Gram of nalgebra's qr()/lu() replacement (CholeskyQR) on the tall
+ * side of single-svdlib's power iteration (call site pca/sparse/mod.rs:170-180).  panel: host m x k row-major, or NULL
+ * for a device-generated normal panel of device_rows rows (timing); avg_ms: average kernel time over iters launches. */
+int salg_op_tall_gram_f32(salg_ctx* ctx, const float* panel, int64_t m, int64_t k, int64_t device_rows, double* gram,
+                          double* colsum, int iters, double* avg_ms);
+
 int salg_op_spmm_bench(salg_ctx* ctx, const salg_csr* csr, int transposed, int64_t k, int iters,
                        double* avg_ms);
 

@@ -4,7 +4,7 @@ from . import _native
 from ._native import SalgError
 from .api import (Context, CsrMatrix, DeviceCsr, Direction, MaskedSparsePCA, MaskedSparsePCABuilder,
                   PowerIterationNormalizer, SVDMethod, SparsePCA, SparsePCABuilder, default_context,
-                  device_count, op_cholqr2, op_small_svd, op_spmm, op_spmm_bench, set_default_context,
+                  device_count, op_cholqr2, op_small_svd, op_spmm, op_spmm_bench, op_tall_gram, set_default_context,
                   synth_device)
 from . import dist, synth
 
@@ -15,5 +15,5 @@ __all__ = [
     "Context", "CsrMatrix", "DeviceCsr", "Direction", "MaskedSparsePCA", "MaskedSparsePCABuilder",
     "PowerIterationNormalizer", "SVDMethod", "SparsePCA", "SparsePCABuilder", "SalgError", "default_context",
     "device_count", "set_default_context", "synth_device", "op_spmm", "op_cholqr2", "op_small_svd",
-    "op_spmm_bench", "dist", "synth", "TRANSFORM_EXACT", "TRANSFORM_REFERENCE_COMPAT",
+    "op_spmm_bench", "op_tall_gram", "dist", "synth", "TRANSFORM_EXACT", "TRANSFORM_REFERENCE_COMPAT",
 ]

@@ -104,6 +104,7 @@ PROTOTYPES = {
     "salg_op_cholqr2_f64": [_P, _P, _i64, _i64, _P, _P],
     "salg_op_small_svd": [_P, _P, _i64, _P, _P, _P],
     "salg_op_spmm_bench": [_P, _P, _int, _i64, _int, C.POINTER(C.c_double)],
+    "salg_op_tall_gram_f32": [_P, _P, _i64, _i64, _i64, _P, _P, _int, C.POINTER(C.c_double)],
 }
 _SPECIAL = {
     "salg_last_error": ([], C.c_char_p),

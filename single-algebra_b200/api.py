@@ -628,6 +628,23 @@ def op_small_svd(a, ctx=None):
     return u, s, vt
 
 
+def op_tall_gram(panel=None, ctx=None, device_rows=0, k=60, iters=0):
+    """Gram matrix and column sums of a tall f32 panel through the fused tcgen05 pass (test / probe hook).
+    Returns (gram k x k f64, colsum k f64, avg kernel ms)."""
+    ctx = ctx or default_context()
+    if panel is not None:
+        panel = np.ascontiguousarray(panel, dtype=np.float32)
+        m, k = panel.shape
+    else:
+        m = 0
+    g = np.empty((k, k), np.float64)
+    cs = np.empty(k, np.float64)
+    ms = C.c_double()
+    N.check(N.load().salg_op_tall_gram_f32(ctx._h, N.ptr(panel) if panel is not None else None, m, k, device_rows,
+                                           N.ptr(g), N.ptr(cs), iters, C.byref(ms)))
+    return g, cs, ms.value
+
+
 def op_spmm_bench(x, transposed=False, k=60, iters=10):
     d = _as_device(x)
     ms = C.c_double()

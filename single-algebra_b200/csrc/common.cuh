@@ -286,6 +286,8 @@ void tc_spmm_A(salg_ctx* ctx, const salg_csr* c, const float* X, float* Y, const
 size_t tc_yprep_bytes(salg_ctx* ctx, const salg_csr* c);
 void tc_gram_prep(salg_ctx* ctx, const salg_csr* c, const float* Y, const unsigned* d_amax, uint8_t* Yprep, float* d_scales,
                   double* G /*GRAM_BUF*/);
+void tc_gram_probe(salg_ctx* ctx, const float* Y, int64_t m, double* G, uint8_t* yprep_out, int iters, double* avg_ms);
+void tc_set_amax(salg_ctx* ctx, unsigned* d_amax, float bound);
 void tc_spmm_At_prepped(salg_ctx* ctx, const salg_csr* c, const uint8_t* Yprep, const float* d_scales, float* Z,
                         const float* mu, const double* corr);
 void tc_spmm_At(salg_ctx* ctx, const salg_csr* c, const float* Y, float* Z, const float* mu, const double* corr);

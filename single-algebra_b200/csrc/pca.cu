@@ -315,9 +315,32 @@ static salg_pca* pca_fit(salg_ctx* ctx, const salg_csr* x, const salg_pca_params
                 spmm_A<T>(ctx, op, Z.get(), Y.get(), center ? corr.get() : nullptr, false);
             }
             // Q = orth(Y); B^T = A_c^T Q
-            cholqr2<T>(ctx, Y.get(), m_loc, l, true, cs.get(), nullptr, d_flag.get(), 2);
-            spmm_At<T>(ctx, op, Y.get(), Z.get(), d_mu, center ? cs.get() : nullptr);
-            allreduce_panel_T<T>(ctx, Z.get(), (size_t)n_eff * LP, center ? d_mu : nullptr, cs.get(), n_eff);
+            bool final_done = false;
+            if constexpr (std::is_same<T, float>::value) {
+                if (fused && !getenv("SALG_NO_FUSED_FINAL")) {
+                    // CholeskyQR2 with the same fused pass: Q1 = Y R1^{-1} explicitly (one read + one write of the panel),
+                    // the second Gram is taken of Q1 while it is pre-split, and R2^{-1} goes to the small side:
+                    // A_c^T Q = (A_c^T Q1) R2^{-1}.  Q itself is never needed (the scores are A_c V).
+                    tc_gram_prep(ctx, op, Y.get(), yamax.get(), Yprep.get(), yscales.get(), Gy.get());
+                    allreduce_f64(ctx, Gy.get(), GRAM_BUF);
+                    chol_inv<T>(ctx, Gy.get(), l, nullptr, nullptr, RiT.get(), d_flag.get());
+                    panel_mul<T>(ctx, Y.get(), m_loc, RiT.get(), Y.get());
+                    tc_set_amax(ctx, yamax.get(), 1.0625f);      // columns of Q1 have norm 1 +- (Gram rounding): |q| <= 1.06
+                    tc_gram_prep(ctx, op, Y.get(), yamax.get(), Yprep.get(), yscales.get(), Gy.get());
+                    allreduce_f64(ctx, Gy.get(), GRAM_BUF);
+                    chol_inv<T>(ctx, Gy.get(), l, nullptr, nullptr, RiT.get(), d_flag.get());
+                    const double* cs1 = Gy.get() + LP * LP;       // 1^T Q1 over all ranks' rows
+                    tc_spmm_At_prepped(ctx, op, Yprep.get(), yscales.get(), Z.get(), d_mu, center ? cs1 : nullptr);
+                    allreduce_panel_T<T>(ctx, Z.get(), (size_t)n_eff * LP, center ? d_mu : nullptr, cs1, n_eff);
+                    panel_mul<T>(ctx, Z.get(), n_eff, RiT.get(), Z.get());
+                    final_done = true;
+                }
+            }
+            if (!final_done) {
+                cholqr2<T>(ctx, Y.get(), m_loc, l, true, cs.get(), nullptr, d_flag.get(), 2);
+                spmm_At<T>(ctx, op, Y.get(), Z.get(), d_mu, center ? cs.get() : nullptr);
+                allreduce_panel_T<T>(ctx, Z.get(), (size_t)n_eff * LP, center ? d_mu : nullptr, cs.get(), n_eff);
+            }
             // B^T = Q_B R_B; R_B = U_R S V_R^T
             cholqr2<T>(ctx, Z.get(), n_eff, l, false, nullptr, Rb.get(), d_flag.get(), 2);
             jacobi_svd64(ctx, Rb.get(), l, Ur.get(), Sr.get(), Vr.get(), d_flag.get());
@@ -748,6 +771,39 @@ int salg_op_small_svd(salg_ctx* ctx, const double* a, int64_t k, double* u, doub
                 if (vt) vt[i * k + j] = hv[j * LP + i];   // vt = V^T
             }
         }
+    });
+}
+
+int salg_op_tall_gram_f32(salg_ctx* ctx, const float* panel, int64_t m, int64_t k, int64_t device_rows, double* gram,
+                          double* colsum, int iters, double* avg_ms) {
+    return guarded([&] {
+        SALG_REQUIRE(ctx && gram && colsum, SALG_ERR_BAD_ARG, "NULL argument");
+        SALG_REQUIRE(k >= 1 && k <= LP, SALG_ERR_UNSUPPORTED, "panel width must be 1..64");
+        SALG_REQUIRE(tc_enabled(ctx), SALG_ERR_UNSUPPORTED, "tensor-core path disabled (SALG_SPMM_IMPL)");
+        SALG_CUDA(cudaSetDevice(ctx->device));
+        cudaStream_t st = ctx->stream;
+        // panel != NULL: host (m x k row-major); panel == NULL: a device-generated normal panel of device_rows rows (probe)
+        const int64_t rows = panel ? m : device_rows;
+        SALG_REQUIRE(rows >= 0, SALG_ERR_BAD_ARG, "negative row count");
+        DevBuf<float> P((size_t)std::max<int64_t>(rows, 1) * LP, st);
+        if (panel) {
+            DevBuf<float> raw((size_t)std::max<int64_t>(rows * k, 1), st);
+            if (rows) SALG_CUDA(cudaMemcpyAsync(raw.get(), panel, (size_t)rows * k * 4, cudaMemcpyHostToDevice, st));
+            panel_pack<float>(ctx, raw.get(), rows, (int)k, P.get());
+            SALG_CUDA(cudaStreamSynchronize(st));
+        } else if (rows) {
+            omega_normal_kernel<<<(unsigned)ceil_div(rows * LP, 256), 256, 0, st>>>(11, rows, (int)k, P.get(), nullptr);
+            ctx->n_launch++;
+            SALG_CUDA(cudaGetLastError());
+        }
+        DevBuf<double> G(GRAM_BUF, st);
+        tc_gram_probe(ctx, P.get(), rows, G.get(), nullptr, iters, avg_ms);
+        std::vector<double> h(GRAM_BUF);
+        SALG_CUDA(cudaMemcpyAsync(h.data(), G.get(), GRAM_BUF * 8, cudaMemcpyDeviceToHost, st));
+        SALG_CUDA(cudaStreamSynchronize(st));
+        for (int64_t i = 0; i < k; i++)
+            for (int64_t j = 0; j < k; j++) gram[i * k + j] = h[i * LP + j];
+        for (int64_t j = 0; j < k; j++) colsum[j] = h[LP * LP + j];
     });
 }
 

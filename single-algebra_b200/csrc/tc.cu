@@ -23,6 +23,7 @@
 //   warp  17     one thread issues tcgen05.mma (M=128, K=16 per instruction) and tcgen05.commit
 //   warps 18-21  epilogue: tcgen05.ld the f32 accumulator, sum the term rows, rescale, store / atomically add
 //   warp  22     entry loader: lane j owns ring slot j, one cp.async.bulk per tile
+#include <algorithm>
 #include <cub/cub.cuh>
 #include <cuda_fp16.h>
 
@@ -53,6 +54,10 @@ constexpr int TC_S_BYTES = 32768;     // sparse operand buffer: 256 x 64 (A X) o
 constexpr int TC_NSB = TC_GROUPS;     // sparse operand buffers: one per scatter group
 constexpr int TC_EPT = (TC_SLOT_ENTRIES + TC_GROUP_THREADS - 1) / TC_GROUP_THREADS;   // ring entries per thread and tile
 constexpr uint32_t TC_SPIN_LIMIT = 1u << 24;
+// suspend-time hint of mbarrier.try_wait: a waiting thread sleeps in hardware until the phase completes (or this many
+// ns pass) instead of re-issuing the poll; with the default hint the ~25 waiting lanes of a CTA were measured to take
+// most of the issue slots of the SM (ncu: 62 % issue utilisation, three quarters of it poll loops)
+constexpr uint32_t TC_WAIT_HINT_NS = 200000u;
 
 struct TcTiles {
     uint2* entries = nullptr;       // [nnz] .x = half byte-offsets in the A X (bits 0-13) and A^T Y (bits 14-27) operand
@@ -91,10 +96,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok)
-            : "r"(addr), "r"(parity)
+            : "r"(addr), "r"(parity), "r"(TC_WAIT_HINT_NS)
             : "memory");
         if (!ok && ++spins > TC_SPIN_LIMIT) __trap();   // never hang the GPU on a protocol bug
     } while (!ok);
@@ -808,7 +813,7 @@ struct GpSmem {
     static constexpr int G_BYTES = LP * G_LD * 8;
     static constexpr int TOTAL = STAGES * STAGE_BYTES + OPS * OP_BYTES + G_BYTES + 128;
 };
-constexpr int GP_CONV_WARPS = 8;
+constexpr int GP_CONV_WARPS = 16;    // (8 warps left the pass latency-bound on the conversion chain: 0.20 ms per 1M-row panel)
 constexpr int GP_W_EPI = GP_CONV_WARPS, GP_W_LOAD = GP_CONV_WARPS + 4, GP_W_MMA = GP_CONV_WARPS + 5,
               GP_W_STORE = GP_CONV_WARPS + 6;
 constexpr int GP_THREADS = (GP_CONV_WARPS + 7) * 32;
@@ -816,7 +821,7 @@ constexpr int GP_DRAIN = 8;
 
 __global__ void __launch_bounds__(GP_THREADS, 1)
 tc_gram_prep_kernel(const float* __restrict__ Y, int64_t m, int n_rb, const float* __restrict__ scales,
-                    uint8_t* __restrict__ Yprep, double* __restrict__ G /* GRAM_BUF, pre-zeroed */) {
+                    uint8_t* __restrict__ Yprep, double* __restrict__ G /* GRAM_BUF, pre-zeroed */, int dbg) {
     // (no integer round trip on this pointer: the compiler must keep seeing the shared address space, or every access
     // below becomes a generic LD/ST; the no-swizzle operand layouts only need 16 B alignment)
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -855,11 +860,13 @@ tc_gram_prep_kernel(const float* __restrict__ Y, int64_t m, int n_rb, const floa
 
     if (warp < GP_CONV_WARPS) {
         // ================= converters: f32 rows -> canonical fp16 two-term operand =================
-        const int mrow = tid & 127;                 // operand row: 2 * column + term
-        const int pc = mrow >> 1, term = mrow & 1;
-        const int half = tid >> 7;                  // K octets [8 half, 8 half + 8)
+        // One item per thread and block: K-octet o (8 rows) x column pair cp -> the four 16 B chunks of operand rows
+        // m = 4cp .. 4cp+3 (column 2cp term 0/1, column 2cp+1 term 0/1), 64 B contiguous.  Both terms come from one load
+        // and one scaling; conversions are done two values at a time (the pass is instruction-issue bound otherwise).
+        static_assert(GP_CONV_WARPS == 16, "one (octet, column pair) item per thread");
+        const int cp = tid & 31, o = tid >> 5;
         const float s = scales[0];
-        double cs = 0.0;
+        double cs0 = 0.0, cs1 = 0.0;
         for (int it = 0; it < n_mine; it++) {
             const int64_t rb = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
             const int stg = it % GpSmem::STAGES, ob = it % GpSmem::OPS;
@@ -868,30 +875,45 @@ tc_gram_prep_kernel(const float* __restrict__ Y, int64_t m, int n_rb, const floa
                 if (it >= GpSmem::OPS) mbar_wait(&op_free[ob], ((it / GpSmem::OPS) - 1) & 1);
             }
             __syncwarp();
-            const float* src = reinterpret_cast<const float*>(sStage + stg * GpSmem::STAGE_BYTES);
-            uint8_t* op = sOp + ob * GpSmem::OP_BYTES;
-            const int64_t rows_left = m - rb * TC_RB;       // rows of this block that exist (the stage's tail is stale)
-            float part = 0.f;
-#pragma unroll 2
-            for (int j = 0; j < 8; j++) {
-                const int o = half * 8 + j;
-                unsigned short h[8];
+            const float2* src = reinterpret_cast<const float2*>(sStage + stg * GpSmem::STAGE_BYTES) + (size_t)(8 * o) * (LP / 2) + cp;
+            const int rows_left = (int)((m - rb * TC_RB < TC_RB) ? m - rb * TC_RB : TC_RB) - 8 * o;   // valid rows of this octet
+            float2 v[8];
 #pragma unroll
-                for (int jj = 0; jj < 8; jj++) {
-                    const int k = 8 * o + jj;
-                    const float v = (k < rows_left) ? src[k * LP + pc] : 0.f;
-                    part += v;
-                    h[jj] = f16_term(v * s, term);
-                }
-                uint4 q;
-                q.x = h[0] | ((uint32_t)h[1] << 16);
-                q.y = h[2] | ((uint32_t)h[3] << 16);
-                q.z = h[4] | ((uint32_t)h[5] << 16);
-                q.w = h[6] | ((uint32_t)h[7] << 16);
-                const uint32_t off = (uint32_t)o * 2048u + (uint32_t)mrow * 16u;    // canon_off(mrow, 8 o, 2048)
-                *reinterpret_cast<uint4*>(op + off) = q;
+            for (int jj = 0; jj < 8; jj++) v[jj] = src[jj * (LP / 2)];
+            if (rows_left < 8) {                      // last block of the panel: the stage's tail is stale
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++)
+                    if (jj >= rows_left) v[jj] = make_float2(0.f, 0.f);
             }
-            if (term == 0) cs += (double)part;
+            float p0 = 0.f, p1 = 0.f;
+            uint32_t w[4][4];                         // [operand row 4cp + r][packed pair of K values]
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const float2 a = v[2 * q], b = v[2 * q + 1];
+                p0 += a.x + b.x;
+                p1 += a.y + b.y;
+                const float ax = a.x * s, bx = b.x * s, ay = a.y * s, by = b.y * s;
+                const __half2 hx = __floats2half2_rn(ax, bx), hy = __floats2half2_rn(ay, by);       // term 0
+                const float2 fx = __half22float2(hx), fy = __half22float2(hy);
+                const __half2 lx = __floats2half2_rn(ax - fx.x, bx - fx.y), ly = __floats2half2_rn(ay - fy.x, by - fy.y);   // term 1
+                w[0][q] = *reinterpret_cast<const uint32_t*>(&hx);
+                w[1][q] = *reinterpret_cast<const uint32_t*>(&lx);
+                w[2][q] = *reinterpret_cast<const uint32_t*>(&hy);
+                w[3][q] = *reinterpret_cast<const uint32_t*>(&ly);
+            }
+            cs0 += (double)p0;
+            cs1 += (double)p1;
+            uint8_t* dst = sOp + ob * GpSmem::OP_BYTES + (uint32_t)o * 2048u + (uint32_t)cp * 64u;   // canon_off(4cp, 8o, 2048)
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const int rr = (r + cp) & 3;          // rotate the chunk order across lanes (bank spread of the 64 B stride)
+                uint4 qv;
+                qv.x = rr == 0 ? w[0][0] : rr == 1 ? w[1][0] : rr == 2 ? w[2][0] : w[3][0];
+                qv.y = rr == 0 ? w[0][1] : rr == 1 ? w[1][1] : rr == 2 ? w[2][1] : w[3][1];
+                qv.z = rr == 0 ? w[0][2] : rr == 1 ? w[1][2] : rr == 2 ? w[2][2] : w[3][2];
+                qv.w = rr == 0 ? w[0][3] : rr == 1 ? w[1][3] : rr == 2 ? w[2][3] : w[3][3];
+                *reinterpret_cast<uint4*>(dst + rr * 16) = qv;
+            }
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
@@ -899,7 +921,8 @@ tc_gram_prep_kernel(const float* __restrict__ Y, int64_t m, int n_rb, const floa
                 mbar_arrive(&st_free[stg]);
             }
         }
-        if (term == 0 && cs != 0.0) atomicAdd(&G[LP * LP + pc], cs);
+        if (cs0 != 0.0) atomicAdd(&G[LP * LP + 2 * cp], cs0);
+        if (cs1 != 0.0) atomicAdd(&G[LP * LP + 2 * cp + 1], cs1);
     } else if (warp == GP_W_LOAD) {
         if (lane == 0) {
             for (int it = 0; it < n_mine; it++) {
@@ -909,6 +932,7 @@ tc_gram_prep_kernel(const float* __restrict__ Y, int64_t m, int n_rb, const floa
                 int64_t rows = m - rb * TC_RB;
                 if (rows > TC_RB) rows = TC_RB;
                 const uint32_t bytes = (uint32_t)rows * LP * 4u;
+                if (dbg & 4) { mbar_arrive(&st_full[stg]); continue; }      // timing experiment: no load
                 mbar_expect_tx(&st_full[stg], bytes);
                 bulk_g2s(sStage + stg * GpSmem::STAGE_BYTES, Y + rb * TC_RB * LP, bytes, &st_full[stg]);
             }
@@ -921,6 +945,7 @@ tc_gram_prep_kernel(const float* __restrict__ Y, int64_t m, int n_rb, const floa
                 const int64_t rb = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
                 const int ob = it % GpSmem::OPS;
                 mbar_wait(&op_full[ob], (it / GpSmem::OPS) & 1);
+                if (dbg & 1) { mbar_arrive(&op_free[ob]); continue; }      // timing experiment: no store
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(Yprep + (size_t)rb * GpSmem::OP_BYTES),
                              "r"(smem_u32(sOp + ob * GpSmem::OP_BYTES)), "r"((uint32_t)GpSmem::OP_BYTES)
                              : "memory");
@@ -943,8 +968,10 @@ tc_gram_prep_kernel(const float* __restrict__ Y, int64_t m, int n_rb, const floa
                 const uint32_t d_tmem = tmem_base + (uint32_t)as * 128u;
                 // K = 128 rows: eight K-steps of 16, both operands are the SAME buffer (P P^T)
                 const uint64_t desc = desc0 + (uint64_t)ob * (GpSmem::OP_BYTES >> 4);
-                umma_f16_run4(d_tmem, desc, desc, idesc, (it % GP_DRAIN) != 0, 256, 256);
-                umma_f16_run4(d_tmem, desc + 1024, desc + 1024, idesc, 1, 256, 256);
+                if (!(dbg & 2)) {                                             // (timing experiment: no MMA)
+                    umma_f16_run4(d_tmem, desc, desc, idesc, (it % GP_DRAIN) != 0, 256, 256);
+                    umma_f16_run4(d_tmem, desc + 1024, desc + 1024, idesc, 1, 256, 256);
+                }
                 umma_commit(&op_free[ob]);
                 if ((it + 1) % GP_DRAIN == 0 || it + 1 == n_mine) umma_commit(&acc_full[as]);
             }
@@ -1190,6 +1217,15 @@ void tc_spmm_A(salg_ctx* ctx, const salg_csr* c, const float* X, float* Y, const
 // Fused pass over a tall panel Y (c->nrows x 64): Yprep = canonical two-term fp16 operand of Y (scale from d_amax, the
 // bits of max |Y| written by tc_spmm_A), d_scales = {s, 1 / (s a_scale)}, G (GRAM_BUF f64) = [Y^T Y, 1^T Y] (local rows).
 size_t tc_yprep_bytes(salg_ctx* ctx, const salg_csr* c) { return (size_t)tiles_of(ctx, c)->n_rb * AtySmem::D_BYTES; }
+__global__ void tc_set_bits_kernel(unsigned* p, unsigned v) { *p = v; }
+// d_amax[0] = bits of a known bound on max |Y| (panels with unit-norm columns: 1)
+void tc_set_amax(salg_ctx* ctx, unsigned* d_amax, float bound) {
+    unsigned bits;
+    memcpy(&bits, &bound, 4);
+    tc_set_bits_kernel<<<1, 1, 0, ctx->stream>>>(d_amax, bits);
+    ctx->n_launch++;
+    SALG_CUDA(cudaGetLastError());
+}
 void tc_gram_prep(salg_ctx* ctx, const salg_csr* c, const float* Y, const unsigned* d_amax, uint8_t* Yprep, float* d_scales,
                   double* G) {
     cudaStream_t st = ctx->stream;
@@ -1202,9 +1238,48 @@ void tc_gram_prep(salg_ctx* ctx, const salg_csr* c, const float* Y, const unsign
     const int n_rb_real = (int)ceil_div(c->nrows, TC_RB);
     SALG_CUDA(cudaFuncSetAttribute(tc_gram_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GpSmem::TOTAL));
     int grid = n_rb_real < ctx->sm_count ? n_rb_real : ctx->sm_count;
-    tc_gram_prep_kernel<<<grid, GP_THREADS, GpSmem::TOTAL, st>>>(Y, c->nrows, n_rb_real, d_scales, Yprep, G);
+    tc_gram_prep_kernel<<<grid, GP_THREADS, GpSmem::TOTAL, st>>>(Y, c->nrows, n_rb_real, d_scales, Yprep, G, 0);
     ctx->n_launch++;
     SALG_CUDA(cudaGetLastError());
+}
+
+// Test / probe entry: G (GRAM_BUF) = [Y^T Y, 1^T Y] of a device panel through the fused pass; returns the average kernel
+// time over `iters` launches.  yprep_out (optional, device, ceil(m/128) * 32 KB) receives the pre-split operand.
+void tc_gram_probe(salg_ctx* ctx, const float* Y, int64_t m, double* G, uint8_t* yprep_out, int iters, double* avg_ms) {
+    cudaStream_t st = ctx->stream;
+    const int n_rb = (int)ceil_div(m, TC_RB);
+    DevBuf<uint8_t> prep(yprep_out ? 0 : (size_t)std::max(n_rb, 1) * GpSmem::OP_BYTES, st);
+    uint8_t* out = yprep_out ? yprep_out : prep.get();
+    DevBuf<float> scales(2, st);
+    DevBuf<unsigned> amax(1, st);
+    SALG_CUDA(cudaMemsetAsync(amax.get(), 0, 4, st));
+    if (m > 0) {
+        int64_t ne = m * LP, want = ceil_div(ne, 256 * 8), cap = (int64_t)ctx->sm_count * 8;
+        tc_absmax_kernel<<<(unsigned)(want < cap ? (want > 0 ? want : 1) : cap), 256, 0, st>>>(Y, ne, amax.get());
+        ctx->n_launch++;
+    }
+    tc_scale_kernel<<<1, 1, 0, st>>>(amax.get(), 1.f, scales.get());
+    ctx->n_launch++;
+    SALG_CUDA(cudaFuncSetAttribute(tc_gram_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GpSmem::TOTAL));
+    const int grid = std::max(1, n_rb < ctx->sm_count ? n_rb : ctx->sm_count);
+    const int dbg = getenv("SALG_GP_DBG") ? atoi(getenv("SALG_GP_DBG")) : 0;
+    cudaEvent_t e0, e1;
+    SALG_CUDA(cudaEventCreate(&e0));
+    SALG_CUDA(cudaEventCreate(&e1));
+    float ms = 0.f;
+    for (int i = 0; i < iters + 1; i++) {          // first launch untimed
+        SALG_CUDA(cudaMemsetAsync(G, 0, GRAM_BUF * sizeof(double), st));
+        if (i == 1) SALG_CUDA(cudaEventRecord(e0, st));
+        tc_gram_prep_kernel<<<grid, GP_THREADS, GpSmem::TOTAL, st>>>(Y, m, n_rb, scales.get(), out, G, dbg);
+        ctx->n_launch++;
+    }
+    SALG_CUDA(cudaEventRecord(e1, st));
+    SALG_CUDA(cudaGetLastError());
+    SALG_CUDA(cudaStreamSynchronize(st));
+    if (iters > 0) SALG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (avg_ms) *avg_ms = iters > 0 ? (double)ms / iters : 0.0;
 }
 
 static void tc_aty_launch(salg_ctx* ctx, const salg_csr* c, TcTiles* t, const uint8_t* Yprep, const float* scales, float* Z);

@@ -118,3 +118,20 @@ def test_tc_products_dense_tiles_and_tiny_shapes(salg, ctx):
             # scale of the un-centred product (a one-row matrix is annihilated by the centring)
             scale = np.abs(_ref_products(A, X, None, transposed)).max()
             assert np.abs(got - ref).max() <= 2e-5 * scale, (shape, dens, transposed)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(1, 5), (127, 60), (128, 64), (1000, 33), (70_001, 60)])
+def test_tall_gram_fused_pass(salg, ctx, shape):
+    """tc_gram_prep_kernel: Gram + column sums of a tall f32 panel (fp16 two-term products on the tensor core, f32
+    accumulation drained to f64 every 1024 rows) against an f64 reference; columns of very different scale."""
+    rng = np.random.default_rng(5)
+    Y = rng.standard_normal(shape).astype(np.float32) * np.logspace(0, -3, shape[1]).astype(np.float32)[None, :]
+    Y[:, 0] += 0.5        # non-zero column mean
+    g, cs, _ = salg.op_tall_gram(Y, ctx)
+    Y64 = Y.astype(np.float64)
+    ref = Y64.T @ Y64
+    nrm = np.sqrt(np.outer(np.diag(ref), np.diag(ref)))
+    assert np.abs(g - ref).max() <= 3e-6 * nrm.max()
+    assert (np.abs(g - ref) <= 2e-5 * nrm + 1e-30).all()          # every entry relative to its own columns' norms
+    assert np.allclose(cs, Y64.sum(axis=0), rtol=1e-6, atol=1e-6 * np.abs(Y64).sum(axis=0).max())
