@@ -166,6 +166,28 @@ int salg_normalize_f64(salg_ctx* ctx, salg_csr* csr, const double* sums, int64_t
                        double target, int direction);
 int salg_normalize_f32_u64(salg_ctx* ctx, salg_csr* csr, const double* sums, int64_t n_sums,
                            double target, int direction);
+/* ---- CSC twins -------------------------------------------------------------------------------------
+ * nalgebra_sparse::CscMatrix<T> = (col_offsets, row_indices, values).  The device handle stores it as the CSR of A^T
+ * (salg_csr_dims reports ncols stored rows); salg_csr_download_* / salg_csr_free / salg_log1p work on it unchanged
+ * (Log1P for CscMatrix, src/sparse/csc.rs:737-746, touches values only). */
+int salg_csc_upload_f32(salg_ctx* ctx, int64_t nrows, int64_t ncols, int64_t nnz, const uint64_t* col_offsets,
+                        const uint64_t* row_indices, const float* values, salg_csr** out);
+int salg_csc_upload_f64(salg_ctx* ctx, int64_t nrows, int64_t ncols, int64_t nnz, const uint64_t* col_offsets,
+                        const uint64_t* row_indices, const double* values, salg_csr** out);
+/* MatrixSum::sum_col / sum_col_squared for CscMatrix (src/sparse/csc.rs:157-197, 323-335): one pass, either output may be
+ * NULL; length ncols. */
+int salg_csc_sum_col_f32(salg_ctx* ctx, const salg_csr* csc, float* sum, float* sumsq);
+int salg_csc_sum_col_f64(salg_ctx* ctx, const salg_csr* csc, double* sum, double* sumsq);
+/* MatrixSum::sum_row for CscMatrix (src/sparse/csc.rs:199-220): scatter over row_indices; length nrows. */
+int salg_csc_sum_row_f32(salg_ctx* ctx, const salg_csr* csc, float* out);
+int salg_csc_sum_row_f64(salg_ctx* ctx, const salg_csr* csc, double* out);
+/* Normalize::normalize for CscMatrix (src/sparse/csc.rs:680-735): `direction` is in terms of A (ROW indexes sums by
+ * row_indices, COLUMN by column), same scale rule as the CSR version. */
+int salg_csc_normalize_f32(salg_ctx* ctx, salg_csr* csc, const float* sums, int64_t n_sums, float target, int direction);
+int salg_csc_normalize_f64(salg_ctx* ctx, salg_csr* csc, const double* sums, int64_t n_sums, double target, int direction);
+int salg_csc_normalize_f32_u64(salg_ctx* ctx, salg_csr* csc, const double* sums, int64_t n_sums, double target,
+                               int direction);
+
 /* Log1P::log1p_normalize (src/sparse/csr.rs:1070-1079): v <- ln(fl(1 + v)). */
 int salg_log1p(salg_ctx* ctx, salg_csr* csr);
 /* Fused sum_row -> normalize(ROW, target) -> log1p -> sum_col/sum_col_squared in one pass over

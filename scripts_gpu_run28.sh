@@ -2,11 +2,9 @@
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q --timeout 600 2>&1 | tail -4
 timeout 300 python scripts_tc_probe.py cfg3 10 2>&1 | tail -2
-SALG_TC_NO_ORDER=1 timeout 300 python scripts_tc_probe.py cfg3 10 2>&1 | tail -2
-timeout 300 python scripts_tc_probe.py cfg2 10 2>&1 | tail -2
-timeout 600 python bench.py --steps 6 --warmup 3 --no-e2e --no-cpu > gpurun_out/b28.log 2> gpurun_out/b28.err; echo "bench exit $?"
+timeout 600 python bench.py --steps 6 --warmup 3 --no-e2e --no-cpu > gpurun_out/b31.log 2> gpurun_out/b31.err; echo "bench exit $?"
 python - <<'PY'
 import json
-d=json.loads(open('gpurun_out/b28.log').read().strip().splitlines()[-1])
+d=json.loads(open('gpurun_out/b31.log').read().strip().splitlines()[-1])
 print(d['ms_per_step'], {k:(round(v['ms_total']/d['steps'],2),v['launches']//d['steps']) for k,v in d['kernel_classes'].items()})
 PY

@@ -2,7 +2,7 @@
 SingleRust/single-algebra behind the reference's own type surface.  See DESIGN.md."""
 from . import _native
 from ._native import SalgError
-from .api import (Context, CsrMatrix, DeviceCsr, Direction, MaskedSparsePCA, MaskedSparsePCABuilder,
+from .api import (Context, CscMatrix, CsrMatrix, DeviceCsr, Direction, MaskedSparsePCA, MaskedSparsePCABuilder,
                   PowerIterationNormalizer, SVDMethod, SparsePCA, SparsePCABuilder, default_context,
                   device_count, op_cholqr2, op_small_svd, op_spmm, op_spmm_bench, op_tall_gram, set_default_context,
                   synth_device)
@@ -12,6 +12,7 @@ TRANSFORM_EXACT = _native.TRANSFORM_EXACT
 TRANSFORM_REFERENCE_COMPAT = _native.TRANSFORM_REFERENCE_COMPAT
 
 __all__ = [
+    "CscMatrix",
     "Context", "CsrMatrix", "DeviceCsr", "Direction", "MaskedSparsePCA", "MaskedSparsePCABuilder",
     "PowerIterationNormalizer", "SVDMethod", "SparsePCA", "SparsePCABuilder", "SalgError", "default_context",
     "device_count", "set_default_context", "synth_device", "op_spmm", "op_cholqr2", "op_small_svd",

@@ -79,6 +79,15 @@ PROTOTYPES = {
     "salg_normalize_f64": [_P, _P, _P, _i64, C.c_double, _int],
     "salg_normalize_f32_u64": [_P, _P, _P, _i64, C.c_double, _int],
     "salg_log1p": [_P, _P],
+    "salg_csc_upload_f32": [_P, _i64, _i64, _i64, _P, _P, _P, C.POINTER(_P)],
+    "salg_csc_upload_f64": [_P, _i64, _i64, _i64, _P, _P, _P, C.POINTER(_P)],
+    "salg_csc_sum_col_f32": [_P, _P, _P, _P],
+    "salg_csc_sum_col_f64": [_P, _P, _P, _P],
+    "salg_csc_sum_row_f32": [_P, _P, _P],
+    "salg_csc_sum_row_f64": [_P, _P, _P],
+    "salg_csc_normalize_f32": [_P, _P, _P, _i64, C.c_float, _int],
+    "salg_csc_normalize_f64": [_P, _P, _P, _i64, C.c_double, _int],
+    "salg_csc_normalize_f32_u64": [_P, _P, _P, _i64, C.c_double, _int],
     "salg_preprocess_f32": [_P, _P, C.c_float, _P, _P],
     "salg_preprocess_f64": [_P, _P, C.c_double, _P, _P],
     "salg_pca_params_default": [C.POINTER(PcaParams)],

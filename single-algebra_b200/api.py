@@ -348,6 +348,105 @@ class CsrMatrix:
         self.values = d.download_values()
 
 
+class CscMatrix:
+    """nalgebra_sparse::CscMatrix<T> (host `col_offsets` / `row_indices` (usize) / `values`) with the reference's
+    MatrixSum / Normalize / Log1P implementations for it (src/sparse/csc.rs:157-220, 323-335, 680-746).  On the device
+    it is the CSR of A^T, so a column of A is a stored row; every method body is one FFI call."""
+
+    def __init__(self, nrows, ncols, col_offsets, row_indices, values, ctx: Optional[Context] = None):
+        self.nrows, self.ncols = int(nrows), int(ncols)
+        self.col_offsets = np.ascontiguousarray(col_offsets, dtype=np.uint64)
+        self.row_indices = np.ascontiguousarray(np.asarray(row_indices).astype(np.uint64, copy=False))
+        v = np.asarray(values)
+        if v.dtype not in (np.float32, np.float64):
+            v = v.astype(np.float64)
+        self.values = np.ascontiguousarray(v)
+        self._ctx = ctx
+        self._h = None
+
+    @classmethod
+    def from_scipy(cls, A, ctx=None):
+        A = A.tocsc()
+        A.sort_indices()
+        return cls(A.shape[0], A.shape[1], A.indptr, A.indices.astype(np.uint64), A.data, ctx)
+
+    @property
+    def dtype(self):
+        return self.values.dtype
+
+    @property
+    def nnz(self):
+        return len(self.values)
+
+    @property
+    def ctx(self):
+        return self._ctx or default_context()
+
+    @property
+    def _sfx(self):
+        return "f64" if self.dtype == np.float64 else "f32"
+
+    def to_device(self):
+        if self._h is None:
+            h = C.c_void_p()
+            N.check(getattr(N.load(), f"salg_csc_upload_{self._sfx}")(
+                self.ctx._h, self.nrows, self.ncols, self.nnz, N.ptr(self.col_offsets), N.ptr(self.row_indices),
+                N.ptr(self.values), C.byref(h)))
+            self._h = h
+        return self._h
+
+    def drop_device(self):
+        if self._h is not None:
+            N.load().salg_csr_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.drop_device()
+        except Exception:
+            pass
+
+    def _refresh_values(self):
+        fn = getattr(N.load(), f"salg_csr_download_{self._sfx}")
+        val = np.empty(self.nnz, self.dtype)
+        N.check(fn(self.ctx._h, self._h, None, None, N.ptr(val)))
+        self.values = val
+
+    # MatrixSum (src/sparse/csc.rs:157-220, 323-335)
+    def sum_col(self):
+        out = np.empty(self.ncols, self.dtype)
+        N.check(getattr(N.load(), f"salg_csc_sum_col_{self._sfx}")(self.ctx._h, self.to_device(), N.ptr(out), None))
+        return out
+
+    def sum_col_squared(self):
+        out = np.empty(self.ncols, self.dtype)
+        N.check(getattr(N.load(), f"salg_csc_sum_col_{self._sfx}")(self.ctx._h, self.to_device(), None, N.ptr(out)))
+        return out
+
+    def sum_row(self):
+        out = np.empty(self.nrows, self.dtype)
+        N.check(getattr(N.load(), f"salg_csc_sum_row_{self._sfx}")(self.ctx._h, self.to_device(), N.ptr(out)))
+        return out
+
+    # Normalize / Log1P (src/sparse/csc.rs:680-746)
+    def normalize(self, sums, target, direction):
+        sums = np.ascontiguousarray(sums)
+        lib, h = N.load(), self.to_device()
+        if self.dtype == np.float64:
+            sums = sums.astype(np.float64, copy=False)
+            N.check(lib.salg_csc_normalize_f64(self.ctx._h, h, N.ptr(sums), len(sums), float(target), direction))
+        elif sums.dtype == np.float64:
+            N.check(lib.salg_csc_normalize_f32_u64(self.ctx._h, h, N.ptr(sums), len(sums), float(target), direction))
+        else:
+            sums = sums.astype(np.float32, copy=False)
+            N.check(lib.salg_csc_normalize_f32(self.ctx._h, h, N.ptr(sums), len(sums), float(target), direction))
+        self._refresh_values()
+
+    def log1p_normalize(self):
+        N.check(N.load().salg_log1p(self.ctx._h, self.to_device()))
+        self._refresh_values()
+
+
 def _as_device(x, ctx=None) -> DeviceCsr:
     return x if isinstance(x, DeviceCsr) else x.to_device(ctx)
 

@@ -439,6 +439,22 @@ int salg_csr_upload_f32(salg_ctx* ctx, int64_t nrows, int64_t ncols, int64_t nnz
         *out = csr_upload<float, uint64_t, uint64_t>(ctx, nrows, ncols, nnz, off, idx, val);
     });
 }
+/* CscMatrix<T> (col_offsets, row_indices, values; src/sparse/csc.rs) is stored as the CSR of A^T: the returned handle has
+ * ncols stored rows.  Same validation as the CSR upload (offsets monotone, indices strictly ascending and in range). */
+int salg_csc_upload_f32(salg_ctx* ctx, int64_t nrows, int64_t ncols, int64_t nnz, const uint64_t* col_off,
+                        const uint64_t* row_idx, const float* val, salg_csr** out) {
+    return guarded([&] {
+        SALG_REQUIRE(out, SALG_ERR_BAD_ARG, "out is NULL");
+        *out = csr_upload<float, uint64_t, uint64_t>(ctx, ncols, nrows, nnz, col_off, row_idx, val);
+    });
+}
+int salg_csc_upload_f64(salg_ctx* ctx, int64_t nrows, int64_t ncols, int64_t nnz, const uint64_t* col_off,
+                        const uint64_t* row_idx, const double* val, salg_csr** out) {
+    return guarded([&] {
+        SALG_REQUIRE(out, SALG_ERR_BAD_ARG, "out is NULL");
+        *out = csr_upload<double, uint64_t, uint64_t>(ctx, ncols, nrows, nnz, col_off, row_idx, val);
+    });
+}
 int salg_csr_upload_f64(salg_ctx* ctx, int64_t nrows, int64_t ncols, int64_t nnz, const uint64_t* off,
                         const uint64_t* idx, const double* val, salg_csr** out) {
     return guarded([&] {

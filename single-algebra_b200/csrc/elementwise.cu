@@ -186,6 +186,19 @@ int salg_normalize_f32_u64(salg_ctx* ctx, salg_csr* c, const double* sums, int64
     return guarded([&] { normalize_api<float, double>(ctx, c, sums, n, target, dir); });
 }
 
+/* CscMatrix::normalize (src/sparse/csc.rs:680-735): same arithmetic; on the stored CSR of A^T the roles of ROW and
+ * COLUMN are exchanged. */
+static int csc_dir(int dir) { return dir == SALG_ROW ? SALG_COLUMN : (dir == SALG_COLUMN ? SALG_ROW : dir); }
+int salg_csc_normalize_f32(salg_ctx* ctx, salg_csr* c, const float* sums, int64_t n, float target, int dir) {
+    return guarded([&] { normalize_api<float, float>(ctx, c, sums, n, target, csc_dir(dir)); });
+}
+int salg_csc_normalize_f64(salg_ctx* ctx, salg_csr* c, const double* sums, int64_t n, double target, int dir) {
+    return guarded([&] { normalize_api<double, double>(ctx, c, sums, n, target, csc_dir(dir)); });
+}
+int salg_csc_normalize_f32_u64(salg_ctx* ctx, salg_csr* c, const double* sums, int64_t n, double target, int dir) {
+    return guarded([&] { normalize_api<float, double>(ctx, c, sums, n, target, csc_dir(dir)); });
+}
+
 int salg_log1p(salg_ctx* ctx, salg_csr* c) {
     return guarded([&] {
         SALG_REQUIRE(ctx && c, SALG_ERR_BAD_ARG, "ctx/csr is NULL");

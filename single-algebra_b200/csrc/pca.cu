@@ -135,7 +135,8 @@ static salg_pca* pca_fit(salg_ctx* ctx, const salg_csr* x, const salg_pca_params
                 fused_compact = tc_enabled(ctx) && prm->svd_method == SALG_SVD_RANDOM && x->nnz > 0 &&
                                 col_stats_can_fuse_compaction(x, (int64_t)run) && !getenv("SALG_NO_FUSED_COMPACT");
             }
-            DevBuf<int> d_ovf(1, st);
+            DevBuf<int> d_ovf(2, st);         // [0] kept-slot overflow, [1] integer-accumulator violation (stats.cu)
+            SALG_CUDA(cudaMemsetAsync(d_ovf.get(), 0, 8, st));
             if (fused_compact) {
                 // row r's slot in the scratch starts at ptr[r] >> shift: 2^-shift >= 3 x the kept fraction of the columns
                 kept_shift = 0;

@@ -165,13 +165,24 @@ col_stats_tiled_kernel(const int64_t* __restrict__ ptr, const uint32_t* __restri
 // every column would need two (and with them a binary search per row and tile).  Warp per row, 8 independent
 // 128 B loads per array in flight per warp; the kept-entry count of the row (the compaction's count pass) rides along.
 // kb = keep bitmask words followed by the exclusive prefix popcounts of the words (rank of a kept column).
-template <typename T>
+// INTSUM: the column sums are accumulated as u32 with the NATIVE shared-memory integer atomic (f32 adds are a
+// compare-and-swap loop, and their rate — not HBM — bounded this pass).  Valid while every value is an integer in
+// [0, 65536) and a CTA sees at most 65536 rows (raw count matrices); any other value raises flags[1] and the caller
+// repeats the pass with f32 accumulators.  Integer sums are exact.
+__global__ void values_integral_probe_kernel(const float* __restrict__ val, int64_t n, int* __restrict__ flag) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = val[i];
+    if (!(x >= 0.f && x < 65536.f && x == truncf(x))) atomicOr(flag, 1);
+}
+
+template <typename T, bool INTSUM>
 __global__ void __launch_bounds__(1024, 1)
 col_stats_masked_kernel(const int64_t* __restrict__ ptr, const uint32_t* __restrict__ col, const T* __restrict__ val,
                         int64_t nrows, int ncols, int n_kept, double* __restrict__ g_sum, double* __restrict__ g_sumsq,
                         const uint32_t* __restrict__ keepbits, unsigned long long* __restrict__ row_kept,
                         uint32_t* __restrict__ kept_col, T* __restrict__ kept_val, int kept_shift,
-                        int* __restrict__ kept_overflow) {
+                        int* __restrict__ flags /* [0] kept-slot overflow, [1] INTSUM violated */) {
     // kept_col / kept_val (optional, (nnz >> kept_shift) + 16 long): the kept entries of row r, renumbered to compact
     // column ids and in their original order, are written from ptr[r] >> kept_shift on — the compaction's WRITE pass
     // fused in as well; the tile builder (tc.cu) consumes them from there, so the 16.8 GB operator is read once, not
@@ -181,15 +192,18 @@ col_stats_masked_kernel(const int64_t* __restrict__ ptr, const uint32_t* __restr
     const int nw32 = (ncols + 31) / 32;
     float* sum = reinterpret_cast<float*>(smem_raw);          // [ncols]
     float* sq = sum + ncols;                                   // [n_kept]
-    unsigned* kb = reinterpret_cast<unsigned*>(sq + n_kept);   // [nw32] bits, [nw32] prefix
-    const unsigned* kpre = kb + nw32;
+    // {mask word, exclusive prefix popcount} pairs: one 8-byte shared-memory lookup per entry (the random-bank lookups
+    // and the accumulator atomics, not HBM, bound this pass)
+    uint2* kb2 = reinterpret_cast<uint2*>(smem_raw + (((size_t)(ncols + n_kept) * 4 + 7) & ~(size_t)7));   // [nw32]
     for (int i = threadIdx.x; i < ncols + n_kept; i += blockDim.x) sum[i] = 0.f;
-    for (int i = threadIdx.x; i < 2 * nw32; i += blockDim.x) kb[i] = keepbits[i];
+    for (int i = threadIdx.x; i < nw32; i += blockDim.x) kb2[i] = make_uint2(keepbits[i], keepbits[nw32 + i]);
     __syncthreads();
     const int64_t per = (nrows + gridDim.x - 1) / gridDim.x;
     const int64_t r0 = (int64_t)blockIdx.x * per, r1 = r0 + per < nrows ? r0 + per : nrows;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     constexpr int U = 8;
+    bool not_int = false;
+    unsigned* sum_u = reinterpret_cast<unsigned*>(sum);
     for (int64_t r = r0 + warp; r < r1; r += nwarp) {
         const int64_t s = ptr[r], e = ptr[r + 1];
         int kept = 0;                                          // warp-uniform running count of kept entries
@@ -213,11 +227,16 @@ col_stats_masked_kernel(const int64_t* __restrict__ ptr, const uint32_t* __restr
                 float x = 0.f;
                 if (cc[u] != 0xFFFFFFFFu) {
                     x = (float)vv[u];
-                    atomicAdd(&sum[cc[u]], x);
-                    const unsigned w = cc[u] >> 5, b = cc[u] & 31u;
-                    const unsigned word = kb[w];
-                    kbit = (word >> b) & 1u;
-                    rank = kpre[w] + __popc(word & ((1u << b) - 1u));
+                    if (INTSUM) {
+                        not_int |= !(x >= 0.f && x < 65536.f && x == truncf(x));
+                        atomicAdd(&sum_u[cc[u]], (unsigned)x);
+                    } else {
+                        atomicAdd(&sum[cc[u]], x);
+                    }
+                    const unsigned b = cc[u] & 31u;
+                    const uint2 wp = kb2[cc[u] >> 5];
+                    kbit = (wp.x >> b) & 1u;
+                    rank = wp.y + __popc(wp.x & ((1u << b) - 1u));
                 }
                 const unsigned bal = __ballot_sync(0xFFFFFFFFu, kbit);
                 if (kbit) {
@@ -235,17 +254,18 @@ col_stats_masked_kernel(const int64_t* __restrict__ ptr, const uint32_t* __restr
         }
         if (lane == 0) {
             row_kept[r] = (unsigned long long)kept;
-            if (kept_col && kept > cap) atomicOr(kept_overflow, 1);
+            if (kept_col && kept > cap) atomicOr(&flags[0], 1);
         }
     }
+    if (INTSUM && not_int) atomicOr(&flags[1], 1);
     __syncthreads();
     for (int i = threadIdx.x; i < ncols; i += blockDim.x) {
-        const float sv = sum[i];
-        if (sv != 0.f) atomicAdd(&g_sum[i], (double)sv);
-        const unsigned w = (unsigned)i >> 5, b = (unsigned)i & 31u;
-        const unsigned word = kb[w];
-        if (g_sumsq && ((word >> b) & 1u)) {
-            const float q = sq[kpre[w] + __popc(word & ((1u << b) - 1u))];
+        const double sv = INTSUM ? (double)sum_u[i] : (double)sum[i];
+        if (sv != 0.0) atomicAdd(&g_sum[i], sv);
+        const unsigned b = (unsigned)i & 31u;
+        const uint2 wp = kb2[(unsigned)i >> 5];
+        if (g_sumsq && ((wp.x >> b) & 1u)) {
+            const float q = sq[wp.y + __popc(wp.x & ((1u << b) - 1u))];
             if (q != 0.f) atomicAdd(&g_sumsq[i], (double)q);
         }
     }
@@ -261,14 +281,51 @@ static void col_stats_launch(salg_ctx* ctx, const salg_csr* c, double* d_sum, do
     int ncols = (int)c->ncols;
     size_t kb_bytes = keepbits ? (size_t)((ncols + 31) / 32) * 4 : 0;
     size_t need = per_col * (size_t)ncols;
-    const size_t need_masked = ((size_t)ncols + (size_t)n_kept) * 4 + 2 * kb_bytes;
+    const size_t need_masked = ((size_t)ncols + (size_t)n_kept) * 4 + 2 * kb_bytes + 8;
     if (keepbits && row_kept && !CNT && sizeof(T) == 4 && need_masked <= kMaxSmem && !getenv("SALG_STATS_TILED")) {
-        auto k = col_stats_masked_kernel<T>;
-        SALG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
         int grid = (int)(c->nrows < ctx->sm_count ? (c->nrows > 0 ? c->nrows : 1) : ctx->sm_count);
-        k<<<grid, 1024, need_masked, st>>>(c->row_ptr, c->col, (const T*)c->val, c->nrows, ncols, (int)n_kept, d_sum, d_sumsq,
-                                           keepbits, (unsigned long long*)row_kept, kept_col, kept_val, kept_shift, kept_overflow);
-        ctx->n_launch++;
+        DevBuf<int> own_flags(kept_overflow ? 0 : 2, st);
+        int* flags = kept_overflow ? kept_overflow : own_flags.get();
+        if (!kept_overflow) SALG_CUDA(cudaMemsetAsync(flags, 0, 8, st));
+        // integer accumulators when the values look like raw counts (probe on a prefix; the kernel re-checks every value)
+        bool try_int = ceil_div(c->nrows, grid) <= 65536 && !getenv("SALG_STATS_NO_INT");
+        if (try_int) {
+            const int64_t np = c->nnz < 65536 ? c->nnz : 65536;
+            values_integral_probe_kernel<<<(unsigned)ceil_div(np, 256), 256, 0, st>>>((const float*)c->val, np, flags + 1);
+            ctx->n_launch++;
+            int h = 0;
+            SALG_CUDA(cudaMemcpyAsync(&h, flags + 1, 4, cudaMemcpyDeviceToHost, st));
+            SALG_CUDA(cudaStreamSynchronize(st));
+            try_int = h == 0;
+            if (h) SALG_CUDA(cudaMemsetAsync(flags + 1, 0, 4, st));
+        }
+        for (int attempt = 0; attempt < 2; attempt++) {
+            if (try_int) {
+                auto k = col_stats_masked_kernel<T, true>;
+                SALG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+                k<<<grid, 1024, need_masked, st>>>(c->row_ptr, c->col, (const T*)c->val, c->nrows, ncols, (int)n_kept, d_sum,
+                                                   d_sumsq, keepbits, (unsigned long long*)row_kept, kept_col, kept_val,
+                                                   kept_shift, flags);
+            } else {
+                auto k = col_stats_masked_kernel<T, false>;
+                SALG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+                k<<<grid, 1024, need_masked, st>>>(c->row_ptr, c->col, (const T*)c->val, c->nrows, ncols, (int)n_kept, d_sum,
+                                                   d_sumsq, keepbits, (unsigned long long*)row_kept, kept_col, kept_val,
+                                                   kept_shift, flags);
+            }
+            ctx->n_launch++;
+            SALG_CUDA(cudaGetLastError());
+            if (!try_int) break;
+            int h = 0;
+            SALG_CUDA(cudaMemcpyAsync(&h, flags + 1, 4, cudaMemcpyDeviceToHost, st));
+            SALG_CUDA(cudaStreamSynchronize(st));
+            if (!h) break;
+            // a non-integral value past the probed prefix: redo with f32 accumulators
+            try_int = false;
+            SALG_CUDA(cudaMemsetAsync(d_sum, 0, (size_t)ncols * 8, st));
+            if (d_sumsq) SALG_CUDA(cudaMemsetAsync(d_sumsq, 0, (size_t)ncols * 8, st));
+            SALG_CUDA(cudaMemsetAsync(flags, 0, 8, st));
+        }
     } else if (kept_col) {
         throw Error(SALG_ERR_UNSUPPORTED, "fused compaction needs the single-tile masked statistics kernel");
     } else if (need <= kMaxSmem && !keepbits) {
@@ -335,10 +392,37 @@ template void col_stats_device<double>(salg_ctx*, const salg_csr*, double*, doub
 // can col_stats_device write the kept entries (kept_col / kept_val) for this matrix / mask?
 bool col_stats_can_fuse_compaction(const salg_csr* c, int64_t n_kept) {
     const size_t kb = (size_t)((c->ncols + 31) / 32) * 4;
-    return c->dtype == SALG_F32 && ((size_t)c->ncols + (size_t)n_kept) * 4 + 2 * kb <= 200 * 1024 && !getenv("SALG_STATS_TILED");
+    return c->dtype == SALG_F32 && ((size_t)c->ncols + (size_t)n_kept) * 4 + 2 * kb + 8 <= 200 * 1024 && !getenv("SALG_STATS_TILED");
 }
 
 // ---- sum_row ----------------------------------------------------------------------------------------------
+// per-row sum and sum of squares (the CSC twins: a column of A is a row of the stored CSR of A^T)
+template <typename T>
+__global__ void sum_row_sq_kernel(const int64_t* __restrict__ ptr, const T* __restrict__ val, int64_t nrows,
+                                  T* __restrict__ out, T* __restrict__ out_sq) {
+    int lane = threadIdx.x & 31;
+    int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = w; r < nrows; r += nw) {
+        int64_t s = ptr[r], e = ptr[r + 1];
+        double a = 0.0, q = 0.0;
+        for (int64_t p = s + lane; p < e; p += 32) {
+            const double v = (double)__ldcs(val + p);
+            a += v;
+            q = fma(v, v, q);
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
+            q += __shfl_xor_sync(0xFFFFFFFFu, q, o);
+        }
+        if (lane == 0) {
+            if (out) out[r] = (T)a;
+            if (out_sq) out_sq[r] = (T)q;
+        }
+    }
+}
+
 template <typename T>
 __global__ void sum_row_kernel(const int64_t* __restrict__ ptr, const T* __restrict__ val, int64_t nrows,
                                T* __restrict__ out) {
@@ -413,6 +497,32 @@ static void sum_row_api(salg_ctx* ctx, const salg_csr* c, T* out) {
     SALG_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
+// CscMatrix::sum_col / sum_col_squared (src/sparse/csc.rs:157-197, 323-335): one pass over the stored rows of A^T
+template <typename T>
+static void csc_sum_col_api(salg_ctx* ctx, const salg_csr* ct, T* sum, T* sumsq) {
+    SALG_REQUIRE(ctx && ct, SALG_ERR_BAD_ARG, "ctx/csc is NULL");
+    SALG_REQUIRE(sum || sumsq, SALG_ERR_BAD_ARG, "sum and sumsq are both NULL");
+    SALG_REQUIRE(ct->dtype == dtype_of<T>::value, SALG_ERR_BAD_ARG, "csc value type does not match the entry point");
+    SALG_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int64_t n = ct->nrows;      // columns of A
+    if (n == 0) return;
+    DevBuf<T> o((size_t)n, st), q((size_t)(sumsq ? n : 0), st);
+    {
+        ProfScope ps(ctx, PROF_STATS, (double)ct->nnz * sizeof(T) + (double)(n + 1) * 8 + (double)n * sizeof(T) * (sumsq ? 2 : 1));
+        int64_t want = ceil_div(n * 32, 256), cap = (int64_t)ctx->sm_count * 16;
+        sum_row_sq_kernel<T><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(ct->row_ptr, (const T*)ct->val, n, o.get(),
+                                                                                 sumsq ? q.get() : nullptr);
+        ctx->n_launch++;
+        SALG_CUDA(cudaGetLastError());
+    }
+    if (ctx->nranks > 1) {   // a CSC handle sharded over ranks holds a block of COLUMNS: nothing to reduce
+    }
+    if (sum) SALG_CUDA(cudaMemcpyAsync(sum, o.get(), (size_t)n * sizeof(T), cudaMemcpyDeviceToHost, st));
+    if (sumsq) SALG_CUDA(cudaMemcpyAsync(sumsq, q.get(), (size_t)n * sizeof(T), cudaMemcpyDeviceToHost, st));
+    SALG_CUDA(cudaStreamSynchronize(st));
+}
+
 __global__ void var_col_kernel(const double* __restrict__ sum, const double* __restrict__ sumsq, double n_rows,
                                double* __restrict__ var, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -451,6 +561,20 @@ int salg_sum_row_f32(salg_ctx* ctx, const salg_csr* c, float* out) {
 }
 int salg_sum_row_f64(salg_ctx* ctx, const salg_csr* c, double* out) {
     return guarded([&] { sum_row_api<double>(ctx, c, out); });
+}
+
+/* CSC twins: the handle holds the CSR of A^T (csc_upload), so a column of A is a stored row */
+int salg_csc_sum_col_f32(salg_ctx* ctx, const salg_csr* csc, float* sum, float* sumsq) {
+    return guarded([&] { csc_sum_col_api<float>(ctx, csc, sum, sumsq); });
+}
+int salg_csc_sum_col_f64(salg_ctx* ctx, const salg_csr* csc, double* sum, double* sumsq) {
+    return guarded([&] { csc_sum_col_api<double>(ctx, csc, sum, sumsq); });
+}
+int salg_csc_sum_row_f32(salg_ctx* ctx, const salg_csr* csc, float* out) {
+    return guarded([&] { sum_col_api<float>(ctx, csc, out, nullptr); });
+}
+int salg_csc_sum_row_f64(salg_ctx* ctx, const salg_csr* csc, double* out) {
+    return guarded([&] { sum_col_api<double>(ctx, csc, out, nullptr); });
 }
 
 int salg_col_stats_f64(salg_ctx* ctx, const salg_csr* c, double* sum, double* sumsq, double* nnz_col,

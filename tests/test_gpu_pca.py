@@ -197,3 +197,22 @@ def test_errors_match_reference_behaviour(salg, ctx):
     # builder defaults (pca/sparse/mod.rs:388-403)
     assert (p.n_components, p.alpha, p.tolerance, p.random_seed, p.center, p.verbose) == (50, 1.0, 1e-6, 42, True, False)
     assert p.svdmethod == salg.SVDMethod.Lanczos
+
+
+def test_masked_statistics_integer_accumulators_fall_back(salg, ctx):
+    """The masked statistics pass accumulates raw counts in integer shared-memory atomics after probing a prefix of the
+    values; a non-integral (or >= 65536, or negative) value past the probed prefix must send it back to f32 accumulators."""
+    A = planted_counts(3000, 700, seed=33, dtype=np.float32).tocsr()
+    assert A.nnz > 70_000
+    for late in (2.5, 70000.0, -3.0):
+        B = A.copy()
+        B.data[-5] = late
+        mask = salg.synth.make_mask(700, 200, seed=7)
+        om = salg.synth.make_omega(200, 30, seed=42, dtype=np.float32)
+        pca = salg.MaskedSparsePCABuilder().n_components(20).mask(mask.tolist()).svd_method(_random(salg=salg)).build()
+        pca.fit(salg.CsrMatrix.from_scipy(B, ctx), omega=om)
+        ref = O.sparse_pca_fit(B.astype(np.float64), 20, omega=om.astype(np.float64), mask=mask, n_oversamples=10,
+                               n_power_iterations=7)
+        assert np.allclose(pca.mean_, ref.mean, rtol=1e-5, atol=1e-7)
+        assert abs(pca.total_var_ - ref.total_var) < 1e-4 * ref.total_var
+        assert O.largest_principal_angle(pca.components_, ref.components) < ANGLE_TOL

@@ -129,3 +129,51 @@ def test_fused_preprocess_matches_reference_chain(salg, ctx, dtype):
     assert _rel(got, v) < (1e-6 if dtype == np.float32 else 1e-14)
     assert _rel(s, O.sum_col(A.indptr, A.indices, v, 260)) < TOL[dtype]
     assert _rel(q, O.sum_col_squared(A.indptr, A.indices, v, 260)) < TOL[dtype]
+
+
+# ---- CSC twins (src/sparse/csc.rs): the reference's CSC known-answer tests run on a CscMatrix ----------
+def test_csc_kat_s1_exact(salg, ctx):
+    k = KAT["KAT-S1"]                                    # csc.rs:1124-1152
+    m = salg.CscMatrix.from_scipy(sp.csc_matrix(np.array(k["dense"])), ctx)
+    assert m.sum_col().tolist() == k["col_sums"]
+    assert m.sum_row().tolist() == k["row_sums"]
+    assert m.sum_col_squared().tolist() == [17.0, 9.0, 29.0]
+
+
+def test_csc_kat_n2_normalize_sums_to_target(salg, ctx):
+    k = KAT["KAT-N2"]                                    # csc.rs:1257-1301
+    D = np.array(k["dense"], dtype=np.float64)
+    for direction, sums, axis in ((salg.Direction.COLUMN, k["col_sums"], 0), (salg.Direction.ROW, k["row_sums"], 1)):
+        m = salg.CscMatrix.from_scipy(sp.csc_matrix(D), ctx)
+        m.normalize(np.array(sums, dtype=np.float64), float(k["target"]), direction)
+        back = sp.csc_matrix((m.values, m.row_indices.astype(np.int64), m.col_offsets.astype(np.int64)), shape=D.shape).toarray()
+        got = back.sum(axis=axis)
+        want = np.where(np.array(sums) > 0, k["target"], 0.0)
+        assert np.abs(got - want).max() < k["tol"]
+
+
+def test_csc_kat_l1_log1p(salg, ctx):
+    k = KAT["KAT-L1"]                                    # csc.rs:1304-1314
+    v = np.array(k["vals"], dtype=np.float64)
+    m = salg.CscMatrix(len(v), 1, [0, len(v)], np.arange(len(v)), v, ctx)
+    m.log1p_normalize()
+    assert np.abs(m.values - np.log(1.0 + v)).max() < k["tol"]
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_csc_twins_match_csr(salg, ctx, dtype):
+    A = planted_counts(700, 300, seed=12, dtype=dtype)
+    c, r = salg.CscMatrix.from_scipy(A, ctx), salg.CsrMatrix.from_scipy(A, ctx)
+    tol = 1e-12 if dtype == np.float64 else 1e-6
+    assert np.allclose(c.sum_col(), r.sum_col(), rtol=tol)
+    assert np.allclose(c.sum_row(), r.sum_row(), rtol=tol)
+    assert np.allclose(c.sum_col_squared(), r.sum_col_squared(), rtol=tol)
+    for direction, n in ((salg.Direction.ROW, 700), (salg.Direction.COLUMN, 300)):
+        sums = np.random.default_rng(3).uniform(0.0, 5.0, n).astype(dtype)
+        sums[::7] = 0.0                                  # scale 0: entries untouched (csc.rs:690-697)
+        c2, r2 = salg.CscMatrix.from_scipy(A, ctx), salg.CsrMatrix.from_scipy(A, ctx)
+        c2.normalize(sums, 100.0, direction)
+        r2.normalize(sums, 100.0, direction)
+        Bc = sp.csc_matrix((c2.values, c2.row_indices.astype(np.int64), c2.col_offsets.astype(np.int64)), shape=A.shape)
+        Br = sp.csr_matrix((r2.values, r2.col_indices.astype(np.int64), r2.row_offsets.astype(np.int64)), shape=A.shape)
+        assert abs(Bc - Br).max() == 0.0                 # same arithmetic on both layouts: bit-identical values
