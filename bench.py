@@ -260,13 +260,18 @@ def run_ours(args, wl):
     peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     classes = {k: {"ms_total": v[0], "launches": v[1], "gbs": (v[2] / v[0] / 1e6) if v[0] > 0 and v[2] > 0 else None}
                for k, v in prof.items()}
+    # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the two product kernels from ONE
+    # `ncu --set full` capture each, on this workload at 1 GPU: profiles/r01_v3_ncu_full_tc_ax_aty.csv
+    ncu_traffic = {("cfg3", "spmm"): 1.122587e9 + 0.238490e9, ("cfg3", "spmm_t"): 1.481904e9 + 0.003990e9}
     dom = max((k for k in ("spmm", "spmm_t") if k in prof), key=lambda k: prof[k][0], default=None)
     roofline = None
     if dom:
         tms, n, b = prof[dom]
         achieved = b / tms / 1e6     # GB/s
         roofline = {"bound": "hbm", "kernel": ("tc_aty_kernel (A^T Y, tcgen05 tile-densified)" if dom == "spmm_t" else "tc_ax_kernel (A X, tcgen05 tile-densified)"),
-                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": ncu_traffic.get((args.workload, dom)) if world == 1 else None,
+                    "traffic_source": "profiles/r01_v3_ncu_full_tc_ax_aty.csv" if world == 1 and (args.workload, dom) in ncu_traffic else None,
                     "peak_source": peak_src, "avg_launch_ms": tms / n, "launches": n,
                     "algorithmic_bytes_per_launch": b / n, "share_of_step": tms / (ms * 1.0)}
 

@@ -69,6 +69,16 @@ void allreduce_f64(salg_ctx* ctx, double* buf, size_t n) {
     SALG_NCCL(ncclAllReduce(buf, buf, n, ncclDouble, ncclSum, ctx->comm, ctx->stream));
 }
 
+// one NCCL launch for the pair (Gram + column sums in f64, partial A^T Y panel in f32) of a power-iteration half step
+void allreduce_gram_and_panel(salg_ctx* ctx, double* gram, size_t n_gram, float* panel, size_t n_panel) {
+    if (ctx->nranks <= 1) return;
+    ProfScope ps(ctx, PROF_ALLREDUCE, (double)n_gram * 8 + (double)n_panel * 4);
+    SALG_NCCL(ncclGroupStart());
+    if (n_gram) SALG_NCCL(ncclAllReduce(gram, gram, n_gram, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+    if (n_panel) SALG_NCCL(ncclAllReduce(panel, panel, n_panel, ncclFloat, ncclSum, ctx->comm, ctx->stream));
+    SALG_NCCL(ncclGroupEnd());
+}
+
 template <>
 void allreduce_T<float>(salg_ctx* ctx, float* buf, size_t n) {
     if (ctx->nranks <= 1 || n == 0) return;

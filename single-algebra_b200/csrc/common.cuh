@@ -310,6 +310,7 @@ template <typename T> void cholqr2(salg_ctx* ctx, T* Y, int64_t m_local, int k, 
                                    double* d_Rtot, int* d_flag, int passes);
 
 void allreduce_f64(salg_ctx* ctx, double* buf, size_t n);
+void allreduce_gram_and_panel(salg_ctx* ctx, double* gram, size_t n_gram, float* panel, size_t n_panel);
 template <typename T> void allreduce_T(salg_ctx* ctx, T* buf, size_t n);
 
 // ---- pca.cu ---------------------------------------------------------------------------------------

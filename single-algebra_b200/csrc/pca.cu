@@ -288,12 +288,13 @@ static salg_pca* pca_fit(salg_ctx* ctx, const salg_csr* x, const salg_pca_params
             for (int it = 0; it < q; it++) {
                 if (fused) {
                     if constexpr (std::is_same<T, float>::value) {
+                        // every rank centres its partial with ITS OWN column sums: sum_r (A_r^T Y_r - mu cs_r^T) is the
+                        // centred product, so the Gram / column sums and the partial panel share one NCCL launch
                         tc_gram_prep(ctx, op, Y.get(), yamax.get(), Yprep.get(), yscales.get(), Gy.get());
-                        allreduce_f64(ctx, Gy.get(), GRAM_BUF);
+                        tc_spmm_At_prepped(ctx, op, Yprep.get(), yscales.get(), Z.get(), d_mu,
+                                           center ? Gy.get() + LP * LP : nullptr);
+                        allreduce_gram_and_panel(ctx, Gy.get(), GRAM_BUF, Z.get(), (size_t)n_eff * LP);
                         chol_inv<T>(ctx, Gy.get(), l, nullptr, nullptr, RiT.get(), d_flag.get());
-                        const double* csy = Gy.get() + LP * LP;          // 1^T Y over all ranks' rows
-                        tc_spmm_At_prepped(ctx, op, Yprep.get(), yscales.get(), Z.get(), d_mu, center ? csy : nullptr);
-                        allreduce_panel_T<T>(ctx, Z.get(), (size_t)n_eff * LP, center ? d_mu : nullptr, csy, n_eff);
                         panel_mul<T>(ctx, Z.get(), n_eff, RiT.get(), Z.get());
                     }
                     cholqr2<T>(ctx, Z.get(), n_eff, l, false, nullptr, nullptr, d_flag.get(), 1);
@@ -328,11 +329,10 @@ static salg_pca* pca_fit(salg_ctx* ctx, const salg_csr* x, const salg_pca_params
                     panel_mul<T>(ctx, Y.get(), m_loc, RiT.get(), Y.get());
                     tc_set_amax(ctx, yamax.get(), 1.0625f);      // columns of Q1 have norm 1 +- (Gram rounding): |q| <= 1.06
                     tc_gram_prep(ctx, op, Y.get(), yamax.get(), Yprep.get(), yscales.get(), Gy.get());
-                    allreduce_f64(ctx, Gy.get(), GRAM_BUF);
+                    tc_spmm_At_prepped(ctx, op, Yprep.get(), yscales.get(), Z.get(), d_mu,
+                                       center ? Gy.get() + LP * LP : nullptr);       // local column sums (see above)
+                    allreduce_gram_and_panel(ctx, Gy.get(), GRAM_BUF, Z.get(), (size_t)n_eff * LP);
                     chol_inv<T>(ctx, Gy.get(), l, nullptr, nullptr, RiT.get(), d_flag.get());
-                    const double* cs1 = Gy.get() + LP * LP;       // 1^T Q1 over all ranks' rows
-                    tc_spmm_At_prepped(ctx, op, Yprep.get(), yscales.get(), Z.get(), d_mu, center ? cs1 : nullptr);
-                    allreduce_panel_T<T>(ctx, Z.get(), (size_t)n_eff * LP, center ? d_mu : nullptr, cs1, n_eff);
                     panel_mul<T>(ctx, Z.get(), n_eff, RiT.get(), Z.get());
                     final_done = true;
                 }

@@ -54,6 +54,37 @@ def _sharded_rsvd(A_loc, n_total, k, p, q, omega):
     return s[:k], vt[:k]
 
 
+def _sharded_rsvd_implicit(A_loc, n_total, k, p, q, omega):
+    """The f32 tensor-core path's schedule (pca.cu, `fused`): the tall panel is never normalised explicitly — one pass
+    gives its Gram matrix and column sums, every rank centres its partial A^T Y with ITS OWN column sums, Gram and
+    partial panel share one all-reduce, and R^{-1} multiplies the small side: A_c^T (Y R^{-1}) = (A_c^T Y) R^{-1}."""
+    mu = _allreduce(np.asarray(A_loc.sum(axis=0)).ravel()) / n_total
+    At = A_loc.T.tocsr()
+    ncols = A_loc.shape[1]
+
+    def half_step(Y):
+        G = Y.T @ Y
+        cs = Y.sum(axis=0)
+        part = At @ Y - mu[:, None] * cs[None, :]            # local centring term only
+        buf = _allreduce(np.concatenate([G.ravel(), part.ravel()]))      # ONE collective
+        l = Y.shape[1]
+        G, Zp = buf[:l * l].reshape(l, l), buf[l * l:].reshape(ncols, l)
+        R = np.linalg.cholesky(G).T
+        return np.linalg.solve(R.T, Zp.T).T, R              # Z' R^{-1}
+
+    Y = A_loc @ omega - (mu @ omega)[None, :]
+    for _ in range(q):
+        Z, _ = half_step(Y)
+        Z, _ = np.linalg.qr(Z)
+        Y = A_loc @ Z - (mu @ Z)[None, :]
+    # final CholeskyQR2: Q1 = Y R1^{-1} explicitly, second Gram of Q1, R2^{-1} on the small side
+    _, R1 = half_step(Y)
+    Q1 = np.linalg.solve(R1.T, Y.T).T
+    Bt, _ = half_step(Q1)
+    _, s, vt = np.linalg.svd(Bt.T, full_matrices=False)
+    return s[:k], vt[:k]
+
+
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
@@ -75,6 +106,9 @@ def _worker(rank, world, port, out):
         u, s_ref, vt_ref = O.randomized_svd(A, 15, 10, 5, om, mean_center=True)
         assert O.rel_err(sv, s_ref) < 1e-9
         assert O.largest_principal_angle(vt, vt_ref) < 1e-6
+        sv2, vt2 = _sharded_rsvd_implicit(A_loc, 900, 15, 10, 5, om)
+        assert O.rel_err(sv2, s_ref) < 1e-9
+        assert O.largest_principal_angle(vt2, vt_ref) < 1e-6
         out.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         out.put((rank, repr(e)))
