@@ -216,3 +216,54 @@ def test_masked_statistics_integer_accumulators_fall_back(salg, ctx):
         assert np.allclose(pca.mean_, ref.mean, rtol=1e-5, atol=1e-7)
         assert abs(pca.total_var_ - ref.total_var) < 1e-4 * ref.total_var
         assert O.largest_principal_angle(pca.components_, ref.components) < ANGLE_TOL
+
+
+def _masked_fit_against_oracle(salg, ctx, A, mask, k, l_extra=10, q=7):
+    n_eff = int(mask.sum())
+    om = salg.synth.make_omega(n_eff, k + l_extra, seed=42, dtype=np.float32)
+    pca = salg.MaskedSparsePCABuilder().n_components(k).mask(mask.tolist()).svd_method(
+        _random(l_extra, q, salg=salg)).build()
+    scores = pca.fit_transform(salg.CsrMatrix.from_scipy(A, ctx), omega=om)
+    ref = O.sparse_pca_fit(A.astype(np.float64), k, omega=om.astype(np.float64), mask=mask, n_oversamples=l_extra,
+                           n_power_iterations=q)
+    return pca, scores, ref
+
+
+def test_fused_compaction_slot_overflow_falls_back(salg, ctx):
+    """The statistics pass writes the kept entries of a row into a slot sized from the GLOBAL kept fraction; a row whose
+    entries all sit in kept columns overflows its slot and the fit must fall back to the separate compaction pass."""
+    A = planted_counts(2500, 800, seed=17, dtype=np.float32).tolil()
+    mask = np.zeros(800, dtype=bool)
+    kept = np.sort(np.random.default_rng(4).choice(800, 40, replace=False))      # 5 % of the columns -> slots = len / 4
+    mask[kept] = True
+    for r in (3, 1200, 2499):                        # rows living entirely inside the kept columns
+        A.rows[r] = kept.tolist()
+        A.data[r] = [float(1 + (j % 5)) for j in range(len(kept))]
+    A = A.tocsr().astype(np.float32)
+    A.sort_indices()
+    pca, scores, ref = _masked_fit_against_oracle(salg, ctx, A, mask, 12)
+    assert O.rel_err(pca.singular_values_, ref.singular_values) < S_TOL_F32
+    assert O.largest_principal_angle(pca.components_, ref.components) < ANGLE_TOL
+    assert np.allclose(pca.mean_, ref.mean, rtol=1e-5, atol=1e-7)
+    ex = O.transform(A, pca.components_, pca.mean_, mask=mask, mode=O.EXACT)
+    assert np.abs(scores - ex).max() < 3e-4 * np.abs(ex).max()
+
+
+@pytest.mark.parametrize("nrows", [70, 129, 1000])
+def test_masked_f32_edge_shapes(salg, ctx, nrows):
+    """Fewer rows than one 128-row tile, one row over, empty rows, rows without any kept entry, a mask keeping fewer
+    columns than one 64-column tile: the fused statistics / tile / Gram passes must agree with the oracle."""
+    A = planted_counts(nrows, 300, density=0.15, seed=nrows, dtype=np.float32).tolil()
+    A.rows[0], A.data[0] = [], []                    # empty rows at both ends
+    A.rows[nrows - 1], A.data[nrows - 1] = [], []
+    A = A.tocsr().astype(np.float32)
+    mask = np.zeros(300, dtype=bool)
+    mask[np.random.default_rng(2).choice(300, 40, replace=False)] = True
+    pca, scores, ref = _masked_fit_against_oracle(salg, ctx, A, mask, 8, l_extra=6, q=4)
+    assert pca.components_.shape == (8, 40)
+    assert O.rel_err(pca.singular_values_, ref.singular_values) < S_TOL_F32
+    assert O.largest_principal_angle(pca.components_, ref.components) < ANGLE_TOL
+    ex = O.transform(A, pca.components_, pca.mean_, mask=mask, mode=O.EXACT)
+    assert scores.shape == (nrows, 8)
+    assert np.abs(scores - ex).max() < 3e-4 * np.abs(ex).max()
+    assert np.abs(scores[0] - ex[0]).max() < 3e-4 * np.abs(ex).max()     # an empty row projects to -mu V
