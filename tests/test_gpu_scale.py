@@ -1,4 +1,4 @@
-"""Full-size checks through size-independent properties (BASELINE configs 2 and 3): device-generated
+"""Full-size checks through size-independent properties (BASELINE configs 2, 3, 4 and one GPU's share of 5): device-generated
 count matrices, adjoint identity of the two sparse products, linearity, checksum of checksums,
 orthonormal components, and a host spot check of the generator."""
 import numpy as np
@@ -95,3 +95,64 @@ def test_config3_masked_fit_properties(salg, ctx):
     assert np.allclose(pca.mean_, s_all / 1e6, rtol=1e-5)
     # parity on a host-regenerable sub-sample is covered by bench.py's cpu_baseline leg and the small tests
     d.free()
+
+
+def test_config4_lanczos_f64_properties(salg, ctx):
+    """BASELINE config 4 at full size: SparsePCA f64, SVDMethod::Lanczos, 250k x 20k at 7 %, 50 components (uncentred
+    operator).  Properties: orthonormal right vectors, descending sigma, ||A v_i|| = sigma_i through the
+    independent product kernel, and agreement of the leading sigma with a randomized fit of the uncentred operator."""
+    spec = salg.synth.make_spec(250_000, 20_000, density=0.07, seed=42)
+    d = salg.synth_device(spec, dtype=np.float64, ctx=ctx)
+    pca = salg.SparsePCABuilder().n_components(50).center(False).build()          # default svd_method = Lanczos
+    pca.fit(d)
+    V = pca.components_
+    s = pca.singular_values_
+    assert V.shape == (50, 20_000) and V.dtype == np.float64
+    assert np.abs(V @ V.T - np.eye(50)).max() < 1e-10
+    assert np.all(np.diff(s) <= 0) and np.all(s > 0)
+    Vp = np.zeros((20_000, 60))
+    Vp[:, :50] = V.T
+    AV = salg.op_spmm(d, Vp)[:, :50]
+    assert np.allclose(np.linalg.norm(AV, axis=0), s, rtol=1e-9)
+    assert np.abs(AV.T @ AV - np.diag(s ** 2)).max() < 1e-8 * s[0] ** 2              # left vectors orthogonal too
+    om = salg.synth.make_omega(20_000, 60, seed=42, dtype=np.float64)
+    rnd = salg.SparsePCABuilder().n_components(50).center(False).svd_method(
+        salg.SVDMethod.Random(10, 7, salg.PowerIterationNormalizer.QR)).build()
+    rnd.fit(d, omega=om)
+    assert O.rel_err(rnd.singular_values_[:10], s[:10]) < 1e-6
+    d.free()
+
+
+def test_config5_shard_preprocessing_properties(salg, ctx):
+    """One GPU's share of BASELINE config 5 (500k x 33k f32 at 7 %): normalize(ROW, 1e4) + log1p + column statistics.
+    Properties: row sums hit the target, expm1 undoes log1p on a host-regenerated sample, the fused pass equals the chain,
+    checksum of checksums."""
+    spec = salg.synth.make_spec(4_000_000, 33_000, density=0.07, seed=42)
+    r0, n = 1_500_000, 500_000
+    d = salg.synth_device(spec, r0, n, dtype=np.float32, ctx=ctx)
+    rs = d.sum_row()
+    assert rs.shape == (n,) and np.all(rs >= 0)
+    d.normalize(rs, 1e4, salg.Direction.ROW)
+    rs2 = d.sum_row().astype(np.float64)
+    nz = rs > 0
+    assert np.abs(rs2[nz] - 1e4).max() < 1e4 * 2e-5 and np.all(rs2[~nz] == 0)
+    d.log1p_normalize()
+    s_chain, q_chain = d.sum_col_and_squared()
+    # host-regenerated sample rows through the same chain in f64
+    ip, ix, dv = salg.synth.generate_rows(spec, r0 + 1234, r0 + 1234 + 48, dtype=np.float32)
+    sub = salg.synth_device(spec, r0 + 1234, 48, dtype=np.float32, ctx=ctx)
+    sub.normalize(sub.sum_row(), 1e4, salg.Direction.ROW)
+    sub.log1p_normalize()
+    _, _, got = sub.download()
+    ref = np.empty(len(dv))
+    for r in range(48):
+        a, b = ip[r], ip[r + 1]
+        tot = dv[a:b].astype(np.float64).sum()
+        ref[a:b] = np.log1p(dv[a:b].astype(np.float64) * (1e4 / tot)) if tot > 0 else dv[a:b]
+    assert np.abs(got - ref).max() < 2e-6 * np.abs(ref).max()
+    # fused preprocess on a fresh copy of the shard equals the chain
+    d2 = salg.synth_device(spec, r0, n, dtype=np.float32, ctx=ctx)
+    s_f, q_f = d2.preprocess(1e4)
+    assert np.allclose(s_f, s_chain, rtol=2e-5, atol=1e-3) and np.allclose(q_f, q_chain, rtol=2e-5, atol=1e-3)
+    assert abs(float(np.sum(s_f, dtype=np.float64)) - float(np.sum(d2.sum_row(), dtype=np.float64))) < 1e-5 * float(np.sum(s_f, dtype=np.float64))
+    d.free(); d2.free(); sub.free()
