@@ -36,8 +36,15 @@ constexpr int TC_CB = 64;           // tile columns
 // The scatter role is latency-bound (barrier hand-offs, shared-memory round trips, proxy fence), not issue-bound, so
 // it is split into independent GROUPS: group g owns sparse-operand buffer g and builds every TC_GROUPS-th unit while the
 // other groups build theirs and the tensor core consumes an earlier one.
+#ifndef TC_GROUP_WARPS_
+#define TC_GROUP_WARPS_ 5
+#endif
+#ifndef TC_UNSCATTER_
+#define TC_UNSCATTER_ 0
+#endif
 constexpr int TC_GROUPS = 3;
-constexpr int TC_GROUP_WARPS = 5;
+constexpr int TC_GROUP_WARPS = TC_GROUP_WARPS_;
+constexpr bool TC_UNSCATTER = TC_UNSCATTER_ != 0;   // zero only what the previous unit wrote instead of clearing the buffer
 constexpr int TC_GROUP_THREADS = TC_GROUP_WARPS * 32;
 constexpr int TC_SCATTER_WARPS = TC_GROUPS * TC_GROUP_WARPS;
 constexpr int TC_NS = 5;              // entry-ring slots (one unit = two tiles each)
@@ -102,6 +109,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "r"(addr), "r"(parity), "r"(TC_WAIT_HINT_NS)
             : "memory");
         if (!ok && ++spins > TC_SPIN_LIMIT) __trap();   // never hang the GPU on a protocol bug
+    } while (!ok);
+}
+// the same wait without the suspend hint, for the two hand-offs that sit on the critical chain of a unit (scatter group
+// <- MMAs retired, MMA issuer <- operand built): waking from a long suspend was measured against polling
+#ifndef TC_FAST_WAITS_
+#define TC_FAST_WAITS_ 0
+#endif
+__device__ __forceinline__ void mbar_wait_crit(uint64_t* bar, uint32_t parity) {
+    if (!TC_FAST_WAITS_) { mbar_wait(bar, parity); return; }
+    uint32_t addr = smem_u32(bar), ok = 0, spins = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (!ok && ++spins > TC_SPIN_LIMIT) __trap();
     } while (!ok);
 }
 // one lane polls, the warp follows
@@ -661,6 +687,10 @@ __device__ __forceinline__ void tc_scatter_role(const uint2* __restrict__ entrie
     const int gt = tid - grp * TC_GROUP_THREADS;           // thread index inside the group
     uint8_t* S = sS + grp * TC_S_BYTES;
     uint32_t lp = 0;                                        // passes this group has built so far
+    uint32_t prev[TC_EPT];                                  // half-offsets this thread wrote for the previous unit (tile 0 | tile 1 << 16)
+#pragma unroll
+    for (int k = 0; k < TC_EPT; k++) prev[k] = 0xFFFFFFFFu;
+    bool full_clear = true;                                 // first unit, or the previous one had entries beyond the slot
     for (int64_t s = grp; s < n_units; s += TC_GROUPS) {
         const int slot = (int)(s % NS);
         const uint32_t slot_use = (uint32_t)(s / NS);
@@ -668,11 +698,20 @@ __device__ __forceinline__ void tc_scatter_role(const uint2* __restrict__ entrie
         const uint2* sl1 = reinterpret_cast<const uint2*>(sRing + (size_t)slot * (2 * TC_SLOT_BYTES) + TC_SLOT_BYTES);
         for (int term = 0; term < a_terms; term++, lp++) {
             if (lane == 0) {
-                if (lp > 0) mbar_wait(&s_free[grp], (lp - 1) & 1);     // the MMAs of this buffer's previous pass have retired
+                if (lp > 0) mbar_wait_crit(&s_free[grp], (lp - 1) & 1);     // the MMAs of this buffer's previous pass have retired
                 if (term == 0) mbar_wait(&e_full[slot], slot_use & 1);
             }
             __syncwarp();
-            for (int i = gt; i < TC_S_BYTES / 16; i += TC_GROUP_THREADS) reinterpret_cast<uint4*>(S)[i] = make_uint4(0, 0, 0, 0);
+            if (!TC_UNSCATTER || (term == 0 && full_clear)) {
+                for (int i = gt; i < TC_S_BYTES / 16; i += TC_GROUP_THREADS) reinterpret_cast<uint4*>(S)[i] = make_uint4(0, 0, 0, 0);
+            } else if (term == 0) {
+#pragma unroll
+                for (int k = 0; k < TC_EPT; k++) {
+                    const uint32_t o0 = prev[k] & 0xFFFFu, o1 = prev[k] >> 16;
+                    if (o0 != 0xFFFFu) *reinterpret_cast<unsigned short*>(S + (o0 << 1)) = 0;
+                    if (o1 != 0xFFFFu) *reinterpret_cast<unsigned short*>(S + (o1 << 1)) = 0;
+                }
+            }   // (a second term overwrites exactly the first term's positions: nothing to clear)
             // this thread's entries of both tiles (independent shared-memory loads, issued before the barrier)
             const int4 mt = *reinterpret_cast<const int4*>(&sMeta[slot].n[0]);     // n0, n1, pad0, pad1
             const int n0 = mt.x, n1 = mt.y;
@@ -685,7 +724,8 @@ __device__ __forceinline__ void tc_scatter_role(const uint2* __restrict__ entrie
                 en0[k] = (i < m0) ? sl0[mt.z + i] : make_uint2(0, 0);
                 en1[k] = (i < m1) ? sl1[mt.w + i] : make_uint2(0, 0);
             }
-            named_bar_sync(1 + grp, TC_GROUP_THREADS);   // every thread's clearing stores precede every scatter store
+            if (!TC_UNSCATTER || term == 0)
+                named_bar_sync(1 + grp, TC_GROUP_THREADS);   // every thread's clearing stores precede every scatter store
 #pragma unroll
             for (int k = 0; k < TC_EPT; k++) {
                 const int i = gt + k * TC_GROUP_THREADS;
@@ -705,6 +745,16 @@ __device__ __forceinline__ void tc_scatter_role(const uint2* __restrict__ entrie
             if (lane == 0) {
                 mbar_arrive(&s_full[grp]);
                 if (term == a_terms - 1) mbar_arrive(&e_free[slot]);   // every lane of this warp has read the slot
+            }
+            if (TC_UNSCATTER && term == a_terms - 1) {
+                full_clear = n0 > lim || n1 > lim;
+#pragma unroll
+                for (int k = 0; k < TC_EPT; k++) {
+                    const int i = gt + k * TC_GROUP_THREADS;
+                    const uint32_t o0 = (i < m0) ? (((ATY ? (en0[k].x >> 14) : en0[k].x) & 0x3FFFu)) : 0xFFFFu;
+                    const uint32_t o1 = (i < m1) ? (((ATY ? (en1[k].x >> 14) : en1[k].x) & 0x3FFFu)) : 0xFFFFu;
+                    prev[k] = o0 | (o1 << 16);
+                }
             }
         }
     }
@@ -806,7 +856,7 @@ tc_ax_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ tile
                     const int sb = it % TC_GROUPS;                           // unit `it` was built by scatter group sb
                     const uint32_t lp0 = (it / TC_GROUPS) * (uint32_t)a_terms;
                     for (int term = 0; term < a_terms; term++) {
-                        mbar_wait(&s_full[sb], (lp0 + term) & 1);
+                        mbar_wait_crit(&s_full[sb], (lp0 + term) & 1);
                         tc_fence_after();
                         TC_T(c_s);
                         // K = 64: four K-steps; dense operand advances 2 chunks x 2048 B, sparse operand 2 x 4096 B
@@ -1179,7 +1229,7 @@ tc_aty_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ til
                     const int sb = unit % TC_GROUPS;                         // built by scatter group sb
                     const uint32_t lp0 = (unit / TC_GROUPS) * (uint32_t)a_terms;
                     for (int term = 0; term < a_terms; term++) {
-                        mbar_wait(&s_full[sb], (lp0 + term) & 1);
+                        mbar_wait_crit(&s_full[sb], (lp0 + term) & 1);
                         tc_fence_after();
                         // K = 128 rows: eight K-steps, both operands advance 2 chunks x 2048 B per step
                         const uint64_t dd = d_desc0 + (uint64_t)bb * (AtySmem::D_BYTES >> 4);
