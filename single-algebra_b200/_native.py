@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsalg_b200.so")
+# SALG_LIB_PATH: load an experiment build of the same library instead (csrc/Makefile: EXTRA / BUILD / OUT)
+LIB_PATH = os.environ.get("SALG_LIB_PATH") and os.path.abspath(os.environ["SALG_LIB_PATH"]) or os.path.join(_HERE, "libsalg_b200.so")
 
 OK, ERR_BAD_ARG, ERR_MASK_LEN, ERR_NOT_FITTED, ERR_CUDA, ERR_NCCL, ERR_NUMERIC, ERR_UNSUPPORTED, ERR_OOM = range(9)
 F32, F64 = 0, 1

@@ -42,12 +42,27 @@ constexpr int TC_CB = 64;           // tile columns
 #ifndef TC_UNSCATTER_
 #define TC_UNSCATTER_ 0
 #endif
-constexpr int TC_GROUPS = 3;
+#ifndef TC_GROUPS_
+#define TC_GROUPS_ 3
+#endif
+#ifndef TC_SLOT_ENTRIES_
+#define TC_SLOT_ENTRIES_ 768
+#endif
+#ifndef TC_NS_
+#define TC_NS_ 5
+#endif
+#ifndef TC_AX_NB_
+#define TC_AX_NB_ 4
+#endif
+#ifndef TC_ATY_NS_
+#define TC_ATY_NS_ TC_NS_
+#endif
+constexpr int TC_GROUPS = TC_GROUPS_;
 constexpr int TC_GROUP_WARPS = TC_GROUP_WARPS_;
 constexpr bool TC_UNSCATTER = TC_UNSCATTER_ != 0;   // zero only what the previous unit wrote instead of clearing the buffer
 constexpr int TC_GROUP_THREADS = TC_GROUP_WARPS * 32;
 constexpr int TC_SCATTER_WARPS = TC_GROUPS * TC_GROUP_WARPS;
-constexpr int TC_NS = 5;              // entry-ring slots (one unit = two tiles each)
+constexpr int TC_NS = TC_NS_;              // entry-ring slots (one unit = two tiles each)
 constexpr int TC_LOADER_WARPS = TC_NS;  // entry loaders: warp w serves units s = w (mod TC_NS), i.e. ALWAYS slot w — a slot's
                                         // uses are then ordered by one thread, so its e_free parity wait can never be a
                                         // whole phase behind (a suspended try_wait parks the whole warp: one lane per warp)
@@ -55,7 +70,7 @@ constexpr int TC_THREADS = (TC_SCATTER_WARPS + 6 + TC_LOADER_WARPS) * 32;   // +
 constexpr int TC_W_BLOAD = TC_SCATTER_WARPS, TC_W_MMA = TC_SCATTER_WARPS + 1, TC_W_EPI = TC_SCATTER_WARPS + 2,
               TC_W_ELOAD = TC_SCATTER_WARPS + 6;
 constexpr int TC_RPAD = 4;            // row blocks are padded to a multiple of this (the A X kernel walks pairs)
-constexpr int TC_SLOT_ENTRIES = 768;  // entries per ring slot (one tile); denser tiles read their tail from global memory
+constexpr int TC_SLOT_ENTRIES = TC_SLOT_ENTRIES_;  // entries per ring slot (one tile); denser tiles read their tail from global memory
 constexpr int TC_SLOT_BYTES = (TC_SLOT_ENTRIES + 2) * 8;
 constexpr int TC_S_BYTES = 32768;     // sparse operand buffer: 256 x 64 (A X) or 128 x 128 (A^T Y) fp16
 constexpr int TC_NSB = TC_GROUPS;     // sparse operand buffers: one per scatter group
@@ -629,10 +644,10 @@ __device__ __forceinline__ void tc_entry_loader(const uint2* __restrict__ entrie
         o[3] = o_two ? tile_ptr[t1 + 1] : 0;
     };
     if (w < nu) fetch(w, p, two);
-    for (int64_t s = w; s < nu; s += TC_LOADER_WARPS) {
+    for (int64_t s = w; s < nu; s += NS) {           // loader w owns ring slot w
         long long np[4] = {0, 0, 0, 0};
         bool ntwo = false;
-        if (s + TC_LOADER_WARPS < nu) fetch(s + TC_LOADER_WARPS, np, ntwo);   // next unit's pointers, overlapped
+        if (s + NS < nu) fetch(s + NS, np, ntwo);   // next unit's pointers, overlapped
         const int slot = (int)(s % NS);
         const uint32_t use = (uint32_t)(s / NS);
         if (use > 0) mbar_wait(&e_free[slot], (use - 1) & 1);
@@ -763,7 +778,7 @@ __device__ __forceinline__ void tc_scatter_role(const uint2* __restrict__ entrie
 // ---- Y = A X - 1 corr^T -----------------------------------------------------------------------------------------------------
 struct AxSmem {
     static constexpr int D_BYTES = 128 * TC_CB * 2;          // 16 KB per stage: panel slice (M = 128) x (K = 64)
-    static constexpr int NB = 4;
+    static constexpr int NB = TC_AX_NB_;
     static constexpr int NS = TC_NS;                         // ring slots
     static constexpr int TOTAL = TC_NSB * TC_S_BYTES + NB * D_BYTES + NS * 2 * TC_SLOT_BYTES + 128;
 };
@@ -817,7 +832,8 @@ tc_ax_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ tile
         tc_scatter_role<false, AxSmem::NS>(entries, seq.n_units(), a_terms, a_scale, sS, sRing, sMeta, e_full, e_free, s_full,
                                            s_free, tid);
     } else if (warp >= TC_W_ELOAD) {
-        if (lane == 0) tc_entry_loader<AxSmem::NS>(entries, tile_ptr, seq, sRing, sMeta, e_full, e_free, warp - TC_W_ELOAD);
+        if (lane == 0 && warp - TC_W_ELOAD < AxSmem::NS)
+            tc_entry_loader<AxSmem::NS>(entries, tile_ptr, seq, sRing, sMeta, e_full, e_free, warp - TC_W_ELOAD);
     } else if (warp == TC_W_BLOAD) {
         // ================= panel-slice loader =================
         if (lane == 0) {
@@ -1144,7 +1160,7 @@ tc_gram_prep_kernel(const float* __restrict__ Y, int64_t m, int n_rb, const floa
 struct AtySmem {
     static constexpr int D_BYTES = 128 * TC_RB * 2;          // 32 KB per stage: Y row block (M = 128) x (K = 128 rows)
     static constexpr int NB = 2;
-    static constexpr int NS = TC_NS;                         // ring slots
+    static constexpr int NS = TC_ATY_NS_;                         // ring slots
     static constexpr int G = 8;                               // operator column blocks per CTA: 4 units x 128 TMEM columns
     static constexpr int TOTAL = TC_NSB * TC_S_BYTES + NB * D_BYTES + NS * 2 * TC_SLOT_BYTES + 128;
 };
@@ -1203,7 +1219,7 @@ tc_aty_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ til
             tc_scatter_role<true, AtySmem::NS>(entries, seq.n_units(), a_terms, a_scale, sS, sRing, sMeta, e_full, e_free, s_full,
                                                s_free, tid);
     } else if (warp >= TC_W_ELOAD) {
-        if (active && lane == 0)
+        if (active && lane == 0 && warp - TC_W_ELOAD < AtySmem::NS)
             tc_entry_loader<AtySmem::NS>(entries, tile_ptr, seq, sRing, sMeta, e_full, e_free, warp - TC_W_ELOAD);
     } else if (warp == TC_W_BLOAD) {
         if (lane == 0 && active) {
