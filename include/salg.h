@@ -237,6 +237,9 @@ int salg_pca_explained_variance_f64(const salg_pca* pca, double* out /* d */);
 /* mean_ : full ncols length (pca/sparse_masked/mod.rs:280-291) */
 int salg_pca_mean_f64(const salg_pca* pca, double* out /* ncols */);
 int salg_pca_total_var(const salg_pca* pca, double* out);
+/* Samples (rows over ALL ranks) the model was fitted on: the n of explained_variance = s^2 / (n - 1)
+ * (pca/sparse/mod.rs:210-216) and of the noise-variance estimate the reference prints (:225-238). */
+int salg_pca_n_samples(const salg_pca* pca, int64_t* out);
 /* bit 1: a Cholesky pivot was floored (rank-deficient panel); bit 2: Jacobi sweep limit reached;
  * bit 4: Lanczos returned before every requested triplet met the acceptance bound */
 int salg_pca_numeric_flags(const salg_pca* pca, int* out);

@@ -102,6 +102,7 @@ PROTOTYPES = {
     "salg_pca_explained_variance_f64": [_P, _P],
     "salg_pca_mean_f64": [_P, _P],
     "salg_pca_total_var": [_P, C.POINTER(C.c_double)],
+    "salg_pca_n_samples": [_P, C.POINTER(_i64)],
     "salg_pca_numeric_flags": [_P, C.POINTER(_int)],
     "salg_pca_transform_f32": [_P, _P, _P, _int, _P],
     "salg_pca_transform_f64": [_P, _P, _P, _int, _P],

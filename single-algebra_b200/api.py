@@ -552,6 +552,9 @@ class _PCABase:
         self.explained_variance_ = ev.astype(self._dtype)
         self.mean_ = mean.astype(self._dtype)
         self.total_var_ = tv.value
+        ns = C.c_int64()
+        N.check(lib.salg_pca_n_samples(h, C.byref(ns)))
+        self._n_samples = ns.value
 
     # -- reference API ------------------------------------------------------------------------------------
     def fit(self, x, omega=None):
@@ -599,6 +602,25 @@ class _PCABase:
     def cumulative_explained_variance_ratio(self):
         """pca/sparse/mod.rs:333-343."""
         return np.cumsum(self.explained_variance_ratio())
+
+    # SURVEY §8f-4: what the reference only prints (pca/sparse/mod.rs:225-238) or normalises by the computed part
+    def explained_variance_ratio_total(self):
+        """explained_variance_ / total variance of the (kept, centred) columns — the scikit-learn definition; the
+        reference divides by the sum over the computed components only (pca/sparse/mod.rs:318-319)."""
+        if self.explained_variance_ is None:
+            raise SalgError(N.ERR_NOT_FITTED, "Must be fitted before transform!")
+        return self.explained_variance_ / self.total_var_
+
+    def noise_variance(self):
+        """(total_var - sum explained) / (min(n_samples, n_features) - n_components): the value the reference prints under
+        `verbose` (pca/sparse/mod.rs:225-238), returned; None when every component was computed."""
+        if self.explained_variance_ is None:
+            raise SalgError(N.ERR_NOT_FITTED, "Must be fitted before transform!")
+        min_dim = min(self._n_samples, self.components_.shape[1])
+        d = len(self.explained_variance_)
+        if d >= min_dim:
+            return None
+        return float((self.total_var_ - self.explained_variance_.sum()) / (min_dim - d))
 
     def numeric_flags(self):
         f = C.c_int()

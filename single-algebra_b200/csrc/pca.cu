@@ -690,6 +690,12 @@ int salg_pca_total_var(const salg_pca* p, double* out) {
         *out = p->total_var;
     });
 }
+int salg_pca_n_samples(const salg_pca* p, int64_t* out) {
+    return guarded([&] {
+        SALG_REQUIRE(p && out, SALG_ERR_BAD_ARG, "NULL argument");
+        *out = p->n_samples;
+    });
+}
 int salg_pca_numeric_flags(const salg_pca* p, int* out) {
     return guarded([&] {
         SALG_REQUIRE(p && out, SALG_ERR_BAD_ARG, "NULL argument");

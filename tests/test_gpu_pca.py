@@ -67,6 +67,22 @@ def test_config1_shape_f64_randomized(salg, ctx):
     assert np.allclose(pca.feature_importances(), pca.components_ ** 2)
 
 
+def test_variance_ratio_against_total_and_noise_variance(salg, ctx):
+    """ratio against the total variance and the noise-variance estimate the reference only prints
+    (pca/sparse/mod.rs:225-238), against a dense computation."""
+    A = planted_counts(1500, 300, seed=9)
+    om = salg.synth.make_omega(300, 30, seed=42, dtype=np.float64)
+    pca = salg.SparsePCABuilder().n_components(20).svd_method(_random(salg=salg)).build()
+    pca.fit(salg.CsrMatrix.from_scipy(A, ctx), omega=om)
+    D = A.toarray()
+    tv = D.var(axis=0, ddof=1).sum()
+    assert abs(pca.total_var_ - tv) < 1e-9 * tv
+    assert np.allclose(pca.explained_variance_ratio_total(), pca.explained_variance_ / tv, rtol=1e-9)
+    assert pca.explained_variance_ratio_total().sum() < 1.0 < pca.explained_variance_ratio().sum() + 1e-12
+    noise = (tv - pca.explained_variance_.sum()) / (min(1500, 300) - 20)
+    assert abs(pca.noise_variance() - noise) < 1e-9 * noise
+
+
 def test_f32_randomized_against_f64_oracle(salg, ctx):
     A = planted_counts(6000, 900, seed=21, dtype=np.float32)
     om = salg.synth.make_omega(900, 40, seed=42, dtype=np.float32)
