@@ -205,7 +205,11 @@ col_stats_masked_kernel(const int64_t* __restrict__ ptr, const uint32_t* __restr
     constexpr int U = 8;
     bool not_int = false;
     unsigned* sum_u = reinterpret_cast<unsigned*>(sum);
-    unsigned long long* sq_u = reinterpret_cast<unsigned long long*>(sq);     // INTSUM: exact integer sums of squares
+    // INTSUM: exact integer sums of squares as two u32 accumulators per kept column (low / high 16 bits of x^2 < 2^32,
+    // each below 2^32 over <= 65536 rows): native atomics, where a 64-bit shared add would be a compare-and-swap loop
+    unsigned* sq_lo = reinterpret_cast<unsigned*>(sq);
+    unsigned* sq_hi = sq_lo + n_kept;
+    unsigned or_bits = 0, or_diff = 0;                          // INTSUM validity, checked once at the end
     // The pass is instruction-issue bound (ncu: 73 % issue utilisation, 82 instructions per entry in the first version), so
     // the body is kept branch-free: lanes past the end of the row add 0 to column 0 instead of diverging, offsets inside
     // a row are 32-bit, and raw counts use native integer atomics for both accumulators (no compare-and-swap loops).
@@ -240,15 +244,21 @@ col_stats_masked_kernel(const int64_t* __restrict__ ptr, const uint32_t* __restr
                 unsigned xi = 0;
                 if (INTSUM) {
                     xi = __float2uint_rz(x);
-                    not_int |= (__uint2float_rn(xi) != x) | (xi > 65535u);
+                    or_bits |= xi;                                                   // any value >= 65536 sets a high bit
+                    or_diff |= __float_as_uint(__uint2float_rn(xi)) ^ __float_as_uint(x);   // any non-integer / negative
                     atomicAdd(&sum_u[cc[u]], xi);
                 } else {
                     atomicAdd(&sum[cc[u]], x);
                 }
                 const unsigned bal = __ballot_sync(0xFFFFFFFFu, kbit);
                 if (kbit) {
-                    if (INTSUM) atomicAdd(&sq_u[rank], (unsigned long long)xi * xi);
-                    else atomicAdd(&sq[rank], x * x);
+                    if (INTSUM) {
+                        const unsigned x2 = xi * xi;
+                        atomicAdd(&sq_lo[rank], x2 & 0xFFFFu);
+                        atomicAdd(&sq_hi[rank], x2 >> 16);
+                    } else {
+                        atomicAdd(&sq[rank], x * x);
+                    }
                     if (kc) {
                         const int k = kept + __popc(bal & ((1u << lane) - 1u));
                         if (k < cap) {
@@ -265,7 +275,7 @@ col_stats_masked_kernel(const int64_t* __restrict__ ptr, const uint32_t* __restr
             if (kept_col && kept > cap) atomicOr(&flags[0], 1);
         }
     }
-    if (INTSUM && not_int) atomicOr(&flags[1], 1);
+    if (INTSUM && (not_int || (or_bits >> 16) != 0u || or_diff != 0u)) atomicOr(&flags[1], 1);
     __syncthreads();
     for (int i = threadIdx.x; i < ncols; i += blockDim.x) {
         const double sv = INTSUM ? (double)sum_u[i] : (double)sum[i];
@@ -274,7 +284,9 @@ col_stats_masked_kernel(const int64_t* __restrict__ ptr, const uint32_t* __restr
         const uint2 wp = kb2[(unsigned)i >> 5];
         if (g_sumsq && ((wp.x >> b) & 1u)) {
             const unsigned k = wp.y + __popc(wp.x & ((1u << b) - 1u));
-            const double q = INTSUM ? (double)reinterpret_cast<const unsigned long long*>(sq)[k] : (double)sq[k];
+            const double q = INTSUM ? (double)reinterpret_cast<const unsigned*>(sq)[k] +
+                                          65536.0 * (double)reinterpret_cast<const unsigned*>(sq)[n_kept + k]
+                                    : (double)sq[k];
             if (q != 0.0) atomicAdd(&g_sumsq[i], q);
         }
     }
