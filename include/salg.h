@@ -95,7 +95,8 @@ int salg_ctx_set_spmm_impl(salg_ctx* ctx, int impl);
 int salg_launch_count(salg_ctx* ctx, int64_t* out);
 
 /* Per-kernel-class device timings (CUDA events on the launching stream), for bench.py's roofline.
- * Classes: see salg_prof_name(). Recording is off by default. */
+ * Classes: see salg_prof_name(). Recording is off by default; on = 1: every class, on = 2: the two sparse-product classes
+ * only (what a timed benchmark region needs for the roofline, without an event pair around every small kernel). */
 int salg_prof_enable(salg_ctx* ctx, int on);
 int salg_prof_reset(salg_ctx* ctx);
 int salg_prof_count(void);

@@ -70,8 +70,10 @@ class Context:
         N.check(N.load().salg_launch_count(self._h, C.byref(n)))
         return n.value
 
-    def prof_enable(self, on=True):
-        N.check(N.load().salg_prof_enable(self._h, 1 if on else 0))
+    def prof_enable(self, on=True, products_only=False):
+        """Per-class CUDA-event timing; `products_only` times just the two sparse-product classes (two event records
+        per product instead of two per scope: the small-side chain of a fit is launch-bound)."""
+        N.check(N.load().salg_prof_enable(self._h, (2 if products_only else 1) if on else 0))
 
     def prof_reset(self):
         N.check(N.load().salg_prof_reset(self._h))

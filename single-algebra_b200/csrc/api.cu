@@ -1,4 +1,5 @@
 // api.cu — context lifecycle, error reporting, profiling records, NCCL plumbing.
+#include <map>
 #include <mutex>
 #include <set>
 
@@ -23,6 +24,7 @@ static const char* kProfNames[PROF_NCLS] = {
 
 ProfScope::ProfScope(salg_ctx* c, int cls, double bytes) : ctx(c) {
     if (!ctx->prof_on) return;
+    if (ctx->prof_products_only && cls != PROF_SPMM && cls != PROF_SPMMT) return;
     ProfRecord r;
     r.cls = cls;
     r.bytes = bytes;
@@ -61,6 +63,19 @@ void prof_collect(salg_ctx* ctx) {
         ctx->event_pool.push_back(r.e1);
     }
     ctx->prof_pending.clear();
+}
+
+void set_max_dyn_smem_impl(const void* kernel, int bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, int> done;      // (kernel, device) -> bytes already granted
+    int dev = 0;
+    SALG_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    int& have = done[{kernel, dev}];
+    if (have < bytes) {
+        SALG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        have = bytes;
+    }
 }
 
 void allreduce_f64(salg_ctx* ctx, double* buf, size_t n) {
@@ -229,6 +244,7 @@ int salg_prof_enable(salg_ctx* c, int on) {
     return guarded([&] {
         SALG_REQUIRE(c, SALG_ERR_BAD_ARG, "ctx is NULL");
         c->prof_on = on != 0;
+        c->prof_products_only = on == 2;     // 2: time only the two sparse-product classes (fewer events in a timed region)
     });
 }
 

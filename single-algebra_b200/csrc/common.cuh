@@ -112,6 +112,7 @@ struct salg_ctx {
     cudaEvent_t timer0 = nullptr, timer1 = nullptr;
     // profiling
     bool prof_on = false;
+    bool prof_products_only = false;
     std::vector<salg::ProfRecord> prof_pending;
     std::vector<cudaEvent_t> event_pool;
     double prof_ms[salg::PROF_NCLS] = {0};
@@ -210,6 +211,12 @@ template <> struct dtype_of<float> { static constexpr int value = SALG_F32; };
 template <> struct dtype_of<double> { static constexpr int value = SALG_F64; };
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per kernel and device instead of before every launch (the
+// power iteration launches ~140 kernels per fit, most of them shorter than the host calls around them)
+void set_max_dyn_smem_impl(const void* kernel, int bytes);   // api.cu
+template <typename K>
+inline void set_max_dyn_smem(K kernel, int bytes) { set_max_dyn_smem_impl((const void*)kernel, bytes); }
 
 // ---- device memory: stream-ordered pool (release threshold = max, see ctx_new) ---------------------------------
 // cudaMalloc / cudaFree synchronise the device and were measured to stall a fit by 10-600 ms on multi-GB buffers;

@@ -179,7 +179,7 @@ chol_inv_kernel(const double* __restrict__ G, int k, double* __restrict__ R, dou
 template <typename T>
 void chol_inv(salg_ctx* ctx, const double* d_G, int k, double* d_R, double* d_Rinv, T* d_RinvT, int* d_flag) {
     ProfScope ps(ctx, PROF_CHOL, 0.0);
-    SALG_CUDA(cudaFuncSetAttribute(chol_inv_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHOL_SMEM));
+    set_max_dyn_smem(chol_inv_kernel<T>, (int)((int)CHOL_SMEM));
     chol_inv_kernel<T><<<1, CHOL_THREADS, CHOL_SMEM, ctx->stream>>>(d_G, k, d_R, d_Rinv, d_RinvT, d_flag);
     ctx->n_launch++;
     SALG_CUDA(cudaGetLastError());
@@ -250,7 +250,7 @@ void panel_mul(salg_ctx* ctx, const T* P, int64_t m, const T* d_M, T* out) {
     int64_t want = ceil_div(m, 64);
     int64_t cap = (int64_t)ctx->sm_count * 4;
     constexpr int kSmem = (int)sizeof(T) * (LP * LP + LP * (64 + 4));
-    SALG_CUDA(cudaFuncSetAttribute(panel_mul_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    set_max_dyn_smem(panel_mul_kernel<T>, (int)(kSmem));
     panel_mul_kernel<T><<<(unsigned)(want < cap ? want : cap), 256, kSmem, ctx->stream>>>(P, m, d_M, out);
     ctx->n_launch++;
     SALG_CUDA(cudaGetLastError());
@@ -277,7 +277,7 @@ __global__ void mat64_mul_kernel(const double* __restrict__ A, const double* __r
 }
 void mat64_mul(salg_ctx* ctx, const double* A, const double* B, double* C) {
     constexpr int kSmem = 2 * LP * (LP + 1) * 8;
-    SALG_CUDA(cudaFuncSetAttribute(mat64_mul_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    set_max_dyn_smem(mat64_mul_kernel, (int)(kSmem));
     mat64_mul_kernel<<<1, 256, kSmem, ctx->stream>>>(A, B, C);
     ctx->n_launch++;
     SALG_CUDA(cudaGetLastError());
@@ -430,7 +430,7 @@ jacobi_svd64_kernel(const double* __restrict__ A, int k, double* __restrict__ U,
 void jacobi_svd64(salg_ctx* ctx, const double* d_A, int k, double* d_U, double* d_S, double* d_V, int* d_flag) {
     ProfScope ps(ctx, PROF_JACOBI, 0.0);
     constexpr int kSmem = 2 * LP * (LP + 1) * 8;
-    SALG_CUDA(cudaFuncSetAttribute(jacobi_svd64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    set_max_dyn_smem(jacobi_svd64_kernel, (int)(kSmem));
     jacobi_svd64_kernel<<<1, 1024, kSmem, ctx->stream>>>(d_A, k, d_U, d_S, d_V, d_flag);
     ctx->n_launch++;
     SALG_CUDA(cudaGetLastError());

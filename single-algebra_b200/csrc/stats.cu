@@ -323,13 +323,13 @@ static void col_stats_launch(salg_ctx* ctx, const salg_csr* c, double* d_sum, do
         for (int attempt = 0; attempt < 2; attempt++) {
             if (try_int) {
                 auto k = col_stats_masked_kernel<T, true>;
-                SALG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+                set_max_dyn_smem(k, (int)((int)kMaxSmem));
                 k<<<grid, 1024, need_masked, st>>>(c->row_ptr, c->col, (const T*)c->val, c->nrows, ncols, (int)n_kept, d_sum,
                                                    d_sumsq, keepbits, (unsigned long long*)row_kept, kept_col, kept_val,
                                                    kept_shift, flags);
             } else {
                 auto k = col_stats_masked_kernel<T, false>;
-                SALG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+                set_max_dyn_smem(k, (int)((int)kMaxSmem));
                 k<<<grid, 1024, need_masked, st>>>(c->row_ptr, c->col, (const T*)c->val, c->nrows, ncols, (int)n_kept, d_sum,
                                                    d_sumsq, keepbits, (unsigned long long*)row_kept, kept_col, kept_val,
                                                    kept_shift, flags);
@@ -351,7 +351,7 @@ static void col_stats_launch(salg_ctx* ctx, const salg_csr* c, double* d_sum, do
         throw Error(SALG_ERR_UNSUPPORTED, "fused compaction needs the single-tile masked statistics kernel");
     } else if (need <= kMaxSmem && !keepbits) {
         auto k = col_stats_flat_kernel<T, A, CNT>;
-        SALG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+        set_max_dyn_smem(k, (int)((int)kMaxSmem));
         int64_t n4 = (c->nnz + 3) / 4;
         int grid = (int)(n4 < (int64_t)ctx->sm_count * 1024 ? ceil_div(n4 > 0 ? n4 : 1, 1024) : ctx->sm_count);
         k<<<grid, 1024, need, st>>>(c->col, (const T*)c->val, c->nnz, ncols, d_sum, d_sumsq, d_cnt);
@@ -364,7 +364,7 @@ static void col_stats_launch(salg_ctx* ctx, const salg_csr* c, double* d_sum, do
         if (n_rb < 1) n_rb = 1;
         if ((int64_t)n_rb > c->nrows) n_rb = (int)(c->nrows > 0 ? c->nrows : 1);
         auto k = col_stats_tiled_kernel<T, A, CNT>;
-        SALG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+        set_max_dyn_smem(k, (int)((int)kMaxSmem));
         if (row_kept && n_tiles > 1) SALG_CUDA(cudaMemsetAsync(row_kept, 0, (size_t)(c->nrows + 1) * 8, st));
         k<<<n_rb * n_tiles, 1024, per_col * (size_t)tile_cols + kb_bytes, st>>>(
             c->row_ptr, c->col, (const T*)c->val, c->nrows, ncols, tile_cols, n_tiles, d_sum, d_sumsq, d_cnt, keepbits,

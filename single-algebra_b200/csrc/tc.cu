@@ -1346,7 +1346,7 @@ void tc_spmm_A(salg_ctx* ctx, const salg_csr* c, const float* X, float* Y, const
     DevBuf<unsigned> amax(1, st);
     tc_prepare_panel<TC_CB>(ctx, X, c->ncols, t->n_cb, t->a_scale, scales.get(), amax.get(), Xprep.get());
     if (d_amax) SALG_CUDA(cudaMemsetAsync(d_amax, 0, 4, st));
-    SALG_CUDA(cudaFuncSetAttribute(tc_ax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AxSmem::TOTAL));
+    set_max_dyn_smem(tc_ax_kernel, (int)(AxSmem::TOTAL));
     int n_pairs = t->n_rb / 2;
     int grid = n_pairs < ctx->sm_count ? n_pairs : ctx->sm_count;
     tc_ax_kernel<<<grid, TC_THREADS, AxSmem::TOTAL, st>>>(t->entries, t->tile_ptr, t->n_rb, t->n_cb, t->a_terms, t->a_scale,
@@ -1379,7 +1379,7 @@ void tc_gram_prep(salg_ctx* ctx, const salg_csr* c, const float* Y, const unsign
     tc_scale_kernel<<<1, 1, 0, st>>>(d_amax, t->a_scale, d_scales);
     ctx->n_launch++;
     const int n_rb_real = (int)ceil_div(c->nrows, TC_RB);
-    SALG_CUDA(cudaFuncSetAttribute(tc_gram_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GpSmem::TOTAL));
+    set_max_dyn_smem(tc_gram_prep_kernel, (int)(GpSmem::TOTAL));
     int grid = n_rb_real < ctx->sm_count ? n_rb_real : ctx->sm_count;
     tc_gram_prep_kernel<<<grid, GP_THREADS, GpSmem::TOTAL, st>>>(Y, c->nrows, n_rb_real, d_scales, Yprep, G, 0);
     ctx->n_launch++;
@@ -1403,7 +1403,7 @@ void tc_gram_probe(salg_ctx* ctx, const float* Y, int64_t m, double* G, uint8_t*
     }
     tc_scale_kernel<<<1, 1, 0, st>>>(amax.get(), 1.f, scales.get());
     ctx->n_launch++;
-    SALG_CUDA(cudaFuncSetAttribute(tc_gram_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GpSmem::TOTAL));
+    set_max_dyn_smem(tc_gram_prep_kernel, (int)(GpSmem::TOTAL));
     const int grid = std::max(1, n_rb < ctx->sm_count ? n_rb : ctx->sm_count);
     const int dbg = getenv("SALG_GP_DBG") ? atoi(getenv("SALG_GP_DBG")) : 0;
     cudaEvent_t e0, e1;
@@ -1469,7 +1469,7 @@ static void tc_aty_launch(salg_ctx* ctx, const salg_csr* c, TcTiles* t, const ui
     if (ranges > n_rb_real) ranges = n_rb_real;
     int rb_per_range = (int)ceil_div(n_rb_real, ranges);
     ranges = (int)ceil_div(n_rb_real, rb_per_range);
-    SALG_CUDA(cudaFuncSetAttribute(tc_aty_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AtySmem::TOTAL));
+    set_max_dyn_smem(tc_aty_kernel, (int)(AtySmem::TOTAL));
     tc_aty_kernel<<<n_groups * ranges, TC_THREADS, AtySmem::TOTAL, st>>>(t->entries, t->tile_ptr, n_rb_real, t->n_cb, t->a_terms,
                                                                          t->a_scale, c->ncols, Yprep, scales, Z,
                                                                          n_groups, rb_per_range);
