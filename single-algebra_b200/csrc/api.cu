@@ -2,6 +2,7 @@
 #include <map>
 #include <mutex>
 #include <set>
+#include <vector>
 
 #include "common.cuh"
 
@@ -63,6 +64,61 @@ void prof_collect(salg_ctx* ctx) {
         ctx->event_pool.push_back(r.e1);
     }
     ctx->prof_pending.clear();
+}
+
+namespace {
+constexpr size_t SMALL_MAX = (size_t)1 << 20;
+constexpr int SMALL_CLASSES = 21;                                  // 2^0 .. 2^20 bytes
+struct SmallCache { std::vector<void*> free_list[SMALL_CLASSES]; };
+std::mutex g_small_mu;
+std::map<cudaStream_t, SmallCache> g_small;
+inline int small_class(size_t bytes) {
+    int c = 8;                                                     // at least 256 B
+    while (((size_t)1 << c) < bytes) c++;
+    return c;
+}
+}  // namespace
+
+void* small_alloc(cudaStream_t s, size_t bytes) {
+    void* p = nullptr;
+    if (bytes <= SMALL_MAX) {
+        const int c = small_class(bytes);
+        {
+            std::lock_guard<std::mutex> lk(g_small_mu);
+            auto& fl = g_small[s].free_list[c];
+            if (!fl.empty()) {
+                p = fl.back();
+                fl.pop_back();
+                return p;
+            }
+        }
+        SALG_CUDA(cudaMallocAsync(&p, (size_t)1 << c, s));
+        return p;
+    }
+    SALG_CUDA(cudaMallocAsync(&p, bytes, s));
+    return p;
+}
+
+void small_free(cudaStream_t s, void* p, size_t bytes) {
+    if (!p) return;
+    if (bytes <= SMALL_MAX) {
+        std::lock_guard<std::mutex> lk(g_small_mu);
+        auto it = g_small.find(s);
+        if (it != g_small.end()) {                                  // (stream already torn down: fall through)
+            it->second.free_list[small_class(bytes)].push_back(p);
+            return;
+        }
+    }
+    cudaFreeAsync(p, s);
+}
+
+void small_cache_release(cudaStream_t s) {
+    std::lock_guard<std::mutex> lk(g_small_mu);
+    auto it = g_small.find(s);
+    if (it == g_small.end()) return;
+    for (auto& fl : it->second.free_list)
+        for (void* p : fl) cudaFreeAsync(p, s);
+    g_small.erase(it);
 }
 
 void set_max_dyn_smem_impl(const void* kernel, int bytes) {
@@ -216,6 +272,7 @@ int salg_ctx_destroy(salg_ctx* c) {
         for (int i = 0; i < salg_ctx::N_STAGE; i++) {
             if (c->stage[i]) cudaFreeHost(c->stage[i]);
             if (i == 0 && c->scratch) cudaFree(c->scratch);
+            if (i == 0 && c->stream) small_cache_release(c->stream);
             if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
         }
         if (c->comm) ncclCommDestroy(c->comm);

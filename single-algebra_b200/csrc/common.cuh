@@ -168,6 +168,13 @@ struct salg_pca {
 namespace salg {
 
 // ---- stream-ordered temporary buffers ------------------------------------------------------------
+// Temporaries up to 1 MB are recycled through a per-stream free list (size classes = powers of two) instead of going
+// back to the CUDA pool: a fit makes ~250 such allocations, and on the launch-bound small-side chain the two runtime
+// calls per buffer were idle time on the GPU.  Reuse is safe because every user of a block is ordered on the one stream
+// the block belongs to.  Larger buffers use cudaMallocAsync / cudaFreeAsync directly.  (api.cu)
+void* small_alloc(cudaStream_t s, size_t bytes);
+void small_free(cudaStream_t s, void* p, size_t bytes);
+void small_cache_release(cudaStream_t s);     // context teardown: hand the cached blocks back to the pool
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
@@ -179,10 +186,10 @@ struct DevBuf {
         release();
         n = n_;
         s = s_;
-        if (n) SALG_CUDA(cudaMallocAsync((void**)&p, n * sizeof(T), s));
+        if (n) p = (T*)small_alloc(s, n * sizeof(T));
     }
     void release() {
-        if (p) cudaFreeAsync(p, s);
+        if (p) small_free(s, p, n * sizeof(T));
         p = nullptr;
         n = 0;
     }
