@@ -277,7 +277,7 @@ def run_ours(args, wl):
                for k, v in merged.items()}
     # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the two product kernels from ONE
     # `ncu --set full` capture each, on this workload at 1 GPU: profiles/r01_v3_ncu_full_tc_ax_aty.csv
-    ncu_traffic = {("cfg3", "spmm"): 1.122587e9 + 0.238490e9, ("cfg3", "spmm_t"): 1.481904e9 + 0.003990e9}
+    ncu_traffic = {("cfg3", "spmm"): 1.122587e9 + 0.238028e9, ("cfg3", "spmm_t"): 1.468230e9 + 0.004183e9}
     dom = max((k for k in ("spmm", "spmm_t") if k in prof), key=lambda k: prof[k][0], default=None)
     roofline = None
     if dom:
