@@ -402,9 +402,14 @@ void col_stats_device(salg_ctx* ctx, const salg_csr* c, double* d_sum, double* d
         }
     }
     // row-sharded context: global column sums
-    allreduce_f64(ctx, d_sum, (size_t)ncols);
-    if (d_sumsq) allreduce_f64(ctx, d_sumsq, (size_t)ncols);
-    if (d_cnt) allreduce_f64(ctx, d_cnt, (size_t)ncols);
+    if (ctx->nranks > 1) {      // one NCCL launch for the two or three vectors
+        ProfScope ps(ctx, PROF_ALLREDUCE, (double)ncols * 8 * (1 + (d_sumsq ? 1 : 0) + (d_cnt ? 1 : 0)));
+        SALG_NCCL(ncclGroupStart());
+        SALG_NCCL(ncclAllReduce(d_sum, d_sum, (size_t)ncols, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+        if (d_sumsq) SALG_NCCL(ncclAllReduce(d_sumsq, d_sumsq, (size_t)ncols, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+        if (d_cnt) SALG_NCCL(ncclAllReduce(d_cnt, d_cnt, (size_t)ncols, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+        SALG_NCCL(ncclGroupEnd());
+    }
 }
 template void col_stats_device<float>(salg_ctx*, const salg_csr*, double*, double*, double*, const uint32_t*, int64_t*, int64_t,
                                       uint32_t*, void*, int, int*);

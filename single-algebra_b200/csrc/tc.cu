@@ -1057,7 +1057,7 @@ tc_gram_prep_kernel(const float* __restrict__ Y, int64_t m, int n_rb, const floa
                 qv.w = rr == 0 ? w[0][3] : rr == 1 ? w[1][3] : rr == 2 ? w[2][3] : w[3][3];
                 *reinterpret_cast<uint4*>(dst + rr * 16) = qv;
             }
-            fence_proxy_async();
+            if (!(dbg & 16)) fence_proxy_async();      // (timing experiment switch)
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(&op_full[ob]);

@@ -283,3 +283,20 @@ def test_masked_f32_edge_shapes(salg, ctx, nrows):
     assert scores.shape == (nrows, 8)
     assert np.abs(scores - ex).max() < 3e-4 * np.abs(ex).max()
     assert np.abs(scores[0] - ex[0]).max() < 3e-4 * np.abs(ex).max()     # an empty row projects to -mu V
+
+
+@pytest.mark.parametrize("q,p_over", [(0, 10), (1, 0), (2, 5)])
+def test_f32_power_iteration_counts(salg, ctx, q, p_over):
+    """n_power_iterations = 0 skips the fused tall-panel path entirely, 1 runs it once; n_oversamples = 0 makes l = k.
+    Same Omega on both sides, so the result must track the oracle for every count."""
+    A = planted_counts(3000, 500, seed=51, dtype=np.float32)
+    k = 12
+    om = salg.synth.make_omega(500, k + p_over, seed=42, dtype=np.float32)
+    pca = salg.SparsePCABuilder().n_components(k).svd_method(_random(p_over, q, salg=salg)).build()
+    pca.fit(salg.CsrMatrix.from_scipy(A, ctx), omega=om)
+    ref = O.sparse_pca_fit(A.astype(np.float64), k, omega=om.astype(np.float64), n_oversamples=p_over, n_power_iterations=q)
+    assert O.rel_err(pca.singular_values_, ref.singular_values) < S_TOL_F32
+    # without power iterations the trailing components of a sketch are ill-determined (both sides compute the same
+    # sketch; their angle is governed by the f32 rounding of tiny gaps), so compare the leading half there
+    lead = k if q > 0 else k // 2
+    assert O.largest_principal_angle(pca.components_[:lead], ref.components[:lead]) < (ANGLE_TOL if q > 0 else 5e-3)
