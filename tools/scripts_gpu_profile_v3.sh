@@ -9,7 +9,7 @@ timeout 600 python bench.py --workload cfg2 --steps 10 --warmup 3 > $O/bench_cfg
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_reference_arm.json 2> $O/bench_ref.err; echo "ref exit $?"
 timeout 600 python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu > $O/plain_launch.log 2>&1 && \
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $O/launches_cfg3.csv python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu > $O/ncu_launch.log 2>&1; echo "ncu launches exit $?"
-timeout 300 python scripts_tc_probe.py cfg3 1 > $O/probe_plain.log 2>&1 && \
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"tc_ax_kernel|tc_aty_kernel" -s 3 -c 2 -o $O/prof_tc -f python scripts_tc_probe.py cfg3 1 > $O/ncu_tc.log 2>&1; echo "ncu tc exit $?"
+timeout 300 python tools/scripts_tc_probe.py cfg3 1 > $O/probe_plain.log 2>&1 && \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"tc_ax_kernel|tc_aty_kernel" -s 3 -c 2 -o $O/prof_tc -f python tools/scripts_tc_probe.py cfg3 1 > $O/ncu_tc.log 2>&1; echo "ncu tc exit $?"
 timeout 900 ncu --set full --clock-control none -k regex:"col_stats_masked|tc_bin_kernel" -s 2 -c 2 -o $O/prof_misc -f python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu > $O/ncu_misc.log 2>&1; echo "ncu misc exit $?"
 python bench_extra.py > $O/extra.log 2>&1; echo "extra exit $?"

@@ -1,5 +1,5 @@
 import os, sys, numpy as np
-sys.path.insert(0, os.getcwd())
+sys.path.insert(0, os.getcwd())   # run from the repo root
 import single_algebra_b200 as s
 ctx = s.default_context()
 spec = s.synth.make_spec(1_000_000, 30_000, density=0.07, seed=42)

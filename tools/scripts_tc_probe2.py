@@ -1,6 +1,6 @@
 """A/B probe of experiment builds of the library: SALG_LIB_PATH=scratch/libsalg_x.so [SALG_TC_ORDER=1] python scripts_tc_probe2.py"""
 import os, sys, numpy as np
-sys.path.insert(0, os.getcwd())
+sys.path.insert(0, os.getcwd())   # run from the repo root
 import single_algebra_b200._native as N
 if os.environ.get("SALG_LIB_PATH"):
     N.LIB_PATH = os.path.abspath(os.environ["SALG_LIB_PATH"])
