@@ -15,65 +15,218 @@ __global__ void make_scale_kernel(const U* __restrict__ sums, U target, U* __res
     }
 }
 
-// ROW: one warp per row; rows whose scale is <= 0 are left untouched (csr.rs:1054-1055)
+// Row streams: one warp per row, kRowU independent 128 B loads in flight per lane array (a B200 SM needs ~40 KB in
+// flight to keep HBM busy; one load per lane and trip left these passes latency bound at ~55 % of the roofline).
+constexpr int kRowU = 16;
+
+// ROW: rows whose scale is <= 0 are left untouched (csr.rs:1054-1055)
 template <typename T, typename U>
 __global__ void normalize_row_kernel(const int64_t* __restrict__ ptr, T* __restrict__ val, int64_t nrows,
                                      const U* __restrict__ scale) {
     int lane = threadIdx.x & 31;
     int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    constexpr int RU = sizeof(T) == 4 ? kRowU : kRowU / 2;
     for (int64_t r = w; r < nrows; r += nw) {
         U sc = scale[r];
         if (!(sc > U(0))) continue;
-        int64_t s = ptr[r], e = ptr[r + 1];
-        for (int64_t p = s + lane; p < e; p += 32) val[p] = (T)((U)val[p] * sc);  // csr.rs:1060
+        const int64_t s = ptr[r];
+        const uint32_t len = (uint32_t)(ptr[r + 1] - s);
+        T* __restrict__ vr = val + s;
+        // whole batches carry no per-load predicate (seven predicate registers would cap the loads in flight at six);
+        // the tail batch clamps its index to the row's last entry and guards the stores
+        uint32_t p0 = 0;
+        for (; p0 + 32 * RU <= len; p0 += 32 * RU) {
+            T v[RU];
+#pragma unroll
+            for (int u = 0; u < RU; u++) v[u] = vr[p0 + lane + 32 * u];
+#pragma unroll
+            for (int u = 0; u < RU; u++) vr[p0 + lane + 32 * u] = (T)((U)v[u] * sc);  // csr.rs:1060
+        }
+        if (p0 < len) {
+            T v[RU];
+            const uint32_t last = len - 1;
+#pragma unroll
+            for (int u = 0; u < RU; u++) {
+                const uint32_t q = p0 + lane + 32 * u;
+                v[u] = vr[q < last ? q : last];
+            }
+            __syncwarp();                                  // every clamped read of the last entry precedes its update
+#pragma unroll
+            for (int u = 0; u < RU; u++) {
+                const uint32_t q = p0 + lane + 32 * u;
+                if (q < len) vr[q] = (T)((U)v[u] * sc);
+            }
+        }
     }
 }
 
-// COLUMN: flat stream, scale gathered by column id (csr.rs:1036-1044)
+// COLUMN: flat stream, 4 entries per thread and trip, scale gathered by column id (csr.rs:1036-1044).
+// The arrays carry 16 entries of slack and start 256 B aligned, so whole quads are loaded; only stores are guarded.
 template <typename T, typename U>
 __global__ void normalize_col_kernel(const uint32_t* __restrict__ col, T* __restrict__ val, int64_t nnz,
                                      const U* __restrict__ scale) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (; i < nnz; i += stride) {
-        U sc = scale[col[i]];
-        if (sc > U(0)) val[i] = (T)((U)val[i] * sc);
+    const int64_t n4 = (nnz + 3) >> 2;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const uint4 c4 = __ldcs(reinterpret_cast<const uint4*>(col) + i);
+        const uint32_t cc[4] = {c4.x, c4.y, c4.z, c4.w};
+        T* v = val + (i << 2);
+        const int64_t left = nnz - (i << 2);
+        if (left >= 4) {
+            T x[4];
+            if (sizeof(T) == 4) {
+                const float4 f = *reinterpret_cast<const float4*>(v);
+                x[0] = (T)f.x; x[1] = (T)f.y; x[2] = (T)f.z; x[3] = (T)f.w;
+            } else {
+                const double2 d0 = *reinterpret_cast<const double2*>(v), d1 = *(reinterpret_cast<const double2*>(v) + 1);
+                x[0] = (T)d0.x; x[1] = (T)d0.y; x[2] = (T)d1.x; x[3] = (T)d1.y;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const U sc = scale[cc[k]];
+                if (sc > U(0)) x[k] = (T)((U)x[k] * sc);
+            }
+            if (sizeof(T) == 4) {
+                *reinterpret_cast<float4*>(v) = make_float4((float)x[0], (float)x[1], (float)x[2], (float)x[3]);
+            } else {
+                *reinterpret_cast<double2*>(v) = make_double2((double)x[0], (double)x[1]);
+                *(reinterpret_cast<double2*>(v) + 1) = make_double2((double)x[2], (double)x[3]);
+            }
+        } else {
+            for (int k = 0; k < (int)left; k++) {
+                const U sc = scale[cc[k]];
+                if (sc > U(0)) v[k] = (T)((U)v[k] * sc);
+            }
+        }
     }
 }
 
-// v <- ln(fl(1 + v)): two roundings in T, not log1p (csr.rs:1074-1075)
+// v <- ln(fl(1 + v)): two roundings in T, not log1p (csr.rs:1074-1075).  128-bit accesses, two quads per
+// thread and trip.
+template <typename T>
+__device__ __forceinline__ T ln_1p_two_step(T v) {
+    const T x = T(1) + v;
+    return (T)log(x);
+}
+
 template <typename T>
 __global__ void log1p_kernel(T* __restrict__ val, int64_t nnz) {
+    constexpr int Q = 16 / sizeof(T);                // entries per 128-bit access
+    const int64_t nq = nnz / Q;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (; i < nnz; i += stride) {
-        T x = T(1) + val[i];
-        val[i] = (T)log(x);
+    if (sizeof(T) == 4) {
+        float4* v4 = reinterpret_cast<float4*>(val);
+        for (; i + stride < nq; i += 2 * stride) {
+            float4 a = v4[i], b = v4[i + stride];
+            a.x = ln_1p_two_step(a.x); a.y = ln_1p_two_step(a.y); a.z = ln_1p_two_step(a.z); a.w = ln_1p_two_step(a.w);
+            b.x = ln_1p_two_step(b.x); b.y = ln_1p_two_step(b.y); b.z = ln_1p_two_step(b.z); b.w = ln_1p_two_step(b.w);
+            v4[i] = a;
+            v4[i + stride] = b;
+        }
+        if (i < nq) {
+            float4 a = v4[i];
+            a.x = ln_1p_two_step(a.x); a.y = ln_1p_two_step(a.y); a.z = ln_1p_two_step(a.z); a.w = ln_1p_two_step(a.w);
+            v4[i] = a;
+        }
+    } else {
+        double2* v2 = reinterpret_cast<double2*>(val);
+        for (; i + stride < nq; i += 2 * stride) {
+            double2 a = v2[i], b = v2[i + stride];
+            a.x = ln_1p_two_step(a.x); a.y = ln_1p_two_step(a.y);
+            b.x = ln_1p_two_step(b.x); b.y = ln_1p_two_step(b.y);
+            v2[i] = a;
+            v2[i + stride] = b;
+        }
+        if (i < nq) {
+            double2 a = v2[i];
+            a.x = ln_1p_two_step(a.x); a.y = ln_1p_two_step(a.y);
+            v2[i] = a;
+        }
     }
+    // tail (< Q entries)
+    const int64_t t = nq * Q + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nnz) val[t] = ln_1p_two_step(val[t]);
 }
 
 // fused row pass: s = sum(row) (f64 accumulate, rounded to T as sum_row returns it),
 // scale = target / s if s > 0 (U = T), v <- ln(1 + T(v * scale)); rows with s <= 0 only get ln(1 + v).
+// Persistent grid of 4 CTAs per SM: the second touch of a row is served by L2 as long as the rows in flight across the
+// chip (one per warp) stay well below its capacity.
 template <typename T>
-__global__ void preprocess_row_kernel(const int64_t* __restrict__ ptr, T* __restrict__ val, int64_t nrows,
-                                      T target) {
+__global__ void __launch_bounds__(256) preprocess_row_kernel(const int64_t* __restrict__ ptr, T* __restrict__ val,
+                                                             int64_t nrows, T target) {
     int lane = threadIdx.x & 31;
     int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    constexpr int RU = sizeof(T) == 4 ? kRowU : kRowU / 2;
     for (int64_t r = w; r < nrows; r += nw) {
-        int64_t s = ptr[r], e = ptr[r + 1];
+        const int64_t s = ptr[r];
+        const uint32_t len = (uint32_t)(ptr[r + 1] - s);
+        T* __restrict__ vr = val + s;
         double a = 0.0;
-        for (int64_t p = s + lane; p < e; p += 32) a += (double)val[p];
+        T v[RU];
+        const uint32_t last = len ? len - 1 : 0;
+        uint32_t p0 = 0;
+        for (; p0 + 32 * RU <= len; p0 += 32 * RU) {       // whole batches: no per-load predicate
+#pragma unroll
+            for (int u = 0; u < RU; u++) v[u] = vr[p0 + lane + 32 * u];
+#pragma unroll
+            for (int u = 0; u < RU; u++) a += (double)v[u];
+        }
+        if (p0 < len) {                                    // tail batch: clamped index, value zeroed afterwards
+#pragma unroll
+            for (int u = 0; u < RU; u++) {
+                const uint32_t q = p0 + lane + 32 * u;
+                v[u] = vr[q < last ? q : last];
+            }
+#pragma unroll
+            for (int u = 0; u < RU; u++) {
+                if (!(p0 + lane + 32 * u < len)) v[u] = T(0);
+                a += (double)v[u];
+            }
+        }
 #pragma unroll
         for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
-        T sum = (T)a;
-        T sc = sum > T(0) ? target / sum : T(0);
-        bool scaled = sc > T(0);
-        for (int64_t p = s + lane; p < e; p += 32) {   // second touch hits L1/L2: the row was just read
-            T v = val[p];
-            if (scaled) v = (T)(v * sc);
-            val[p] = (T)log(T(1) + v);
+        const T sum = (T)a;
+        const T sc = sum > T(0) ? target / sum : T(0);
+        const bool scaled = sc > T(0);
+        if (len <= 32 * RU) {                              // the whole row is still in registers (v of the only batch)
+#pragma unroll
+            for (int u = 0; u < RU; u++) {
+                const uint32_t q = lane + 32 * u;
+                T x = v[u];
+                if (scaled) x = (T)(x * sc);
+                if (q < len) vr[q] = ln_1p_two_step(x);
+            }
+            continue;
+        }
+        // second touch: L1 / L2, the row was just read
+        for (p0 = 0; p0 + 32 * RU <= len; p0 += 32 * RU) {
+#pragma unroll
+            for (int u = 0; u < RU; u++) v[u] = vr[p0 + lane + 32 * u];
+#pragma unroll
+            for (int u = 0; u < RU; u++) {
+                T x = v[u];
+                if (scaled) x = (T)(x * sc);
+                vr[p0 + lane + 32 * u] = ln_1p_two_step(x);
+            }
+        }
+        if (p0 < len) {
+#pragma unroll
+            for (int u = 0; u < RU; u++) {
+                const uint32_t q = p0 + lane + 32 * u;
+                v[u] = vr[q < last ? q : last];
+            }
+            __syncwarp();                                  // every clamped read of the last entry precedes its update
+#pragma unroll
+            for (int u = 0; u < RU; u++) {
+                const uint32_t q = p0 + lane + 32 * u;
+                T x = v[u];
+                if (scaled) x = (T)(x * sc);
+                if (q < len) vr[q] = ln_1p_two_step(x);
+            }
         }
     }
 }
@@ -110,7 +263,7 @@ static void normalize_api(salg_ctx* ctx, salg_csr* c, const U* sums, int64_t n_s
     } else {
         ProfScope ps(ctx, PROF_ELEMENTWISE,
                      2.0 * (double)c->nnz * sizeof(T) + (double)c->nnz * 4 + (double)c->ncols * sizeof(U));
-        normalize_col_kernel<T, U><<<flat_grid(ctx, c->nnz, 256), 256, 0, st>>>(c->col, (T*)c->val, c->nnz,
+        normalize_col_kernel<T, U><<<flat_grid(ctx, (c->nnz + 3) / 4, 256), 256, 0, st>>>(c->col, (T*)c->val, c->nnz,
                                                                                 d_scale.get());
         ctx->n_launch++;
     }
@@ -124,7 +277,7 @@ static void log1p_api(salg_ctx* ctx, salg_csr* c) {
     if (c->nnz == 0) return;
     {
         ProfScope ps(ctx, PROF_ELEMENTWISE, 2.0 * (double)c->nnz * sizeof(T));
-        log1p_kernel<T><<<flat_grid(ctx, c->nnz, 256), 256, 0, ctx->stream>>>((T*)c->val, c->nnz);
+        log1p_kernel<T><<<flat_grid(ctx, c->nnz / (16 / sizeof(T)) + 16, 256), 256, 0, ctx->stream>>>((T*)c->val, c->nnz);
         ctx->n_launch++;
         SALG_CUDA(cudaGetLastError());
     }
@@ -146,8 +299,9 @@ static void preprocess_api(salg_ctx* ctx, salg_csr* c, T target, T* col_sum, T* 
     cudaStream_t st = ctx->stream;
     if (c->nrows && c->nnz) {
         ProfScope ps(ctx, PROF_ELEMENTWISE, 2.0 * (double)c->nnz * sizeof(T) + (double)(c->nrows + 1) * 8);
-        preprocess_row_kernel<T><<<flat_grid(ctx, c->nrows * 32, 256), 256, 0, st>>>(c->row_ptr, (T*)c->val,
-                                                                                     c->nrows, target);
+        int64_t want = ceil_div(c->nrows * 32, 256), cap = (int64_t)ctx->sm_count * 4;
+        preprocess_row_kernel<T><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(c->row_ptr, (T*)c->val, c->nrows,
+                                                                                      target);
         ctx->n_launch++;
         SALG_CUDA(cudaGetLastError());
     }

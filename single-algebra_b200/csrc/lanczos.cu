@@ -16,16 +16,58 @@
 namespace salg {
 
 // ---- SpMV: y = S x, S as CSR arrays --------------------------------------------------------------------------
+// partial dot product of one row for thread `tid` of `NT` cooperating threads: U independent index / value loads in
+// flight per thread, then U gathers of x.  Whole batches carry no per-load predicate (ptxas has seven predicate
+// registers: predicated loads go out six at a time); the tail batch clamps its index to the row's last entry.
+template <typename T, int NT>
+__device__ __forceinline__ double row_dot_partial(const uint32_t* __restrict__ ir, const T* __restrict__ vr, uint32_t len,
+                                                  const T* __restrict__ x, int tid) {
+    constexpr int U = 8;
+    double a = 0.0;
+    uint32_t p0 = 0;
+    for (; p0 + NT * U <= len; p0 += NT * U) {
+        uint32_t c[U];
+        T v[U], xv[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            c[u] = __ldcs(ir + p0 + tid + NT * u);
+            v[u] = __ldcs(vr + p0 + tid + NT * u);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) xv[u] = __ldg(x + c[u]);
+#pragma unroll
+        for (int u = 0; u < U; u++) a = fma((double)v[u], (double)xv[u], a);
+    }
+    if (p0 < len) {
+        uint32_t c[U];
+        T v[U], xv[U];
+        const uint32_t last = len - 1;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            uint32_t q = p0 + tid + NT * u;
+            q = q < last ? q : last;
+            c[u] = __ldcs(ir + q);
+            v[u] = __ldcs(vr + q);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) xv[u] = __ldg(x + c[u]);
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if (p0 + tid + NT * u < len) a = fma((double)v[u], (double)xv[u], a);
+    }
+    return a;
+}
+
 template <typename T>
-__global__ void spmv_warp_kernel(const int64_t* __restrict__ ptr, const uint32_t* __restrict__ idx,
-                                 const T* __restrict__ val, int64_t nr, const T* __restrict__ x, T* __restrict__ y) {
+__global__ void __launch_bounds__(256, 3)
+spmv_warp_kernel(const int64_t* __restrict__ ptr, const uint32_t* __restrict__ idx, const T* __restrict__ val,
+                 int64_t nr, const T* __restrict__ x, T* __restrict__ y) {
     int lane = threadIdx.x & 31;
     int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t r = w; r < nr; r += nw) {
-        int64_t s = ptr[r], e = ptr[r + 1];
-        double a = 0.0;
-        for (int64_t p = s + lane; p < e; p += 32) a = fma((double)__ldcs(val + p), (double)__ldg(x + __ldcs(idx + p)), a);
+        const int64_t s = ptr[r];
+        double a = row_dot_partial<T, 32>(idx + s, val + s, (uint32_t)(ptr[r + 1] - s), x, lane);
 #pragma unroll
         for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
         if (lane == 0) y[r] = (T)a;
@@ -34,16 +76,14 @@ __global__ void spmv_warp_kernel(const int64_t* __restrict__ ptr, const uint32_t
 
 // one CTA per row, for operands whose rows are long and skewed (gene rows of the transposed copy)
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 spmv_block_kernel(const int64_t* __restrict__ ptr, const uint32_t* __restrict__ idx, const T* __restrict__ val,
                   int64_t nr, const T* __restrict__ x, T* __restrict__ y) {
     __shared__ double part[8];
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int64_t r = blockIdx.x; r < nr; r += gridDim.x) {
-        int64_t s = ptr[r], e = ptr[r + 1];
-        double a = 0.0;
-        for (int64_t p = s + threadIdx.x; p < e; p += 256)
-            a = fma((double)__ldcs(val + p), (double)__ldg(x + __ldcs(idx + p)), a);
+        const int64_t s = ptr[r];
+        double a = row_dot_partial<T, 256>(idx + s, val + s, (uint32_t)(ptr[r + 1] - s), x, (int)threadIdx.x);
 #pragma unroll
         for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
         __syncthreads();

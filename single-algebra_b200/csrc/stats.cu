@@ -7,11 +7,50 @@
 // with 128-bit loads and flushes the tile once with f64 global atomics, so the HBM stream is the
 // only large traffic: algorithmic bytes = nnz*(S+I) + 2*ncols*S  (SURVEY §8d).
 #include "common.cuh"
+#include <type_traits>
 
 namespace salg {
 
 template <typename A>
 __device__ __forceinline__ void smem_add(A* p, A v) { atomicAdd(p, v); }
+
+// {sum, sumsq} of one column live side by side.  Shared-memory floating-point adds are compare-and-swap loops
+// (ATOMS.CAST.SPIN; only integer adds are native).
+#ifndef STATS_MHOIST_
+#define STATS_MHOIST_ 0     // batch the mask lookups ahead of the atomics: measured 3 % slower (64 registers)
+#endif
+// The shared-memory atomic unit retires ~2 lane-operations per clock and SM whatever the operation (native integer add
+// or the compare-and-swap loop of a floating-point add: measured 1.9-2.0 per clock in all three kernels below), which
+// caps a one-atomic-per-entry pass at ~72 % of the HBM roofline; these passes run at 90 % of THAT bound.  Measured
+// alternatives, both worse (profiles/r01_v4_summary.md): STATS_L2_SLOTS_ of every 8 entries bypass shared memory and go to
+// the f64 global accumulators as L2 reductions (REDG.ADD.F64) — the chip-wide L2 atomic rate is only ~1e11 per second,
+// 1 slot: +-0, 2 slots: +35 %, 3 slots: +75 % time; STATS_PAIR64_: {sum, sumsq} updated by one 64-bit compare-and-swap
+// loop instead of two 32-bit ones — ATOMS.CAST.SPIN.64 is ~8x slower per operation (4.1 -> 15.6 ms).
+#ifndef STATS_L2_SLOTS_
+#define STATS_L2_SLOTS_ 0
+#endif
+#ifndef STATS_PAIR64_
+#define STATS_PAIR64_ 0
+#endif
+__device__ __forceinline__ void pair_add(float* pair, float x) {
+#if STATS_PAIR64_
+    unsigned long long* a = reinterpret_cast<unsigned long long*>(pair);
+    unsigned long long old = *a, assumed;
+    do {
+        assumed = old;
+        const float s = __uint_as_float((unsigned)assumed) + x;
+        const float q = fmaf(x, x, __uint_as_float((unsigned)(assumed >> 32)));
+        old = atomicCAS(a, assumed, ((unsigned long long)__float_as_uint(q) << 32) | __float_as_uint(s));
+    } while (old != assumed);
+#else
+    atomicAdd(pair, x);
+    atomicAdd(pair + 1, x * x);
+#endif
+}
+__device__ __forceinline__ void pair_add(double* pair, double x) {
+    atomicAdd(pair, x);
+    atomicAdd(pair + 1, x * x);
+}
 
 // ---- variant 1: the whole column range fits one shared-memory tile: flat stream over the entries ------
 template <typename T, typename A, bool CNT>
@@ -25,32 +64,51 @@ col_stats_flat_kernel(const uint32_t* __restrict__ col, const T* __restrict__ va
     if (CNT) for (int i = threadIdx.x; i < ncols; i += blockDim.x) cnt[i] = 0u;
     __syncthreads();
 
-    // contiguous chunk per CTA, 4 entries per thread per step (the arrays carry 16 entries of slack)
+    // contiguous chunk per CTA; 2 x 4 entries per thread per step, all loads issued before the first atomic
+    // (the arrays carry 16 entries of slack)
     int64_t n4 = (nnz + 3) >> 2;
     int64_t per = (n4 + gridDim.x - 1) / gridDim.x;
     int64_t b0 = (int64_t)blockIdx.x * per, b1 = b0 + per;
     if (b1 > n4) b1 = n4;
     const uint4* col4 = reinterpret_cast<const uint4*>(col);
-    for (int64_t i = b0 + threadIdx.x; i < b1; i += blockDim.x) {
-        uint4 c = __ldcs(col4 + i);
-        T v[4];
-        if (sizeof(T) == 4) {
-            float4 f = __ldcs(reinterpret_cast<const float4*>(val) + i);
-            v[0] = (T)f.x; v[1] = (T)f.y; v[2] = (T)f.z; v[3] = (T)f.w;
-        } else {
-            double2 d0 = __ldcs(reinterpret_cast<const double2*>(val) + 2 * i);
-            double2 d1 = __ldcs(reinterpret_cast<const double2*>(val) + 2 * i + 1);
-            v[0] = (T)d0.x; v[1] = (T)d0.y; v[2] = (T)d1.x; v[3] = (T)d1.y;
-        }
-        uint32_t cc[4] = {c.x, c.y, c.z, c.w};
-        int64_t e = i << 2;
+    constexpr int UF = 2;
+    for (int64_t i0 = b0 + threadIdx.x; i0 < b1; i0 += (int64_t)UF * blockDim.x) {
+        uint32_t cc[UF][4];
+        T v[UF][4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            if (e + k < nnz) {
-                A x = (A)v[k];
-                smem_add(&acc[2 * cc[k]], x);
-                smem_add(&acc[2 * cc[k] + 1], x * x);
-                if (CNT) atomicAdd(&cnt[cc[k]], 1u);
+        for (int u = 0; u < UF; u++) {
+            const int64_t i = i0 + (int64_t)u * blockDim.x;
+            if (i < b1) {
+                const uint4 c = __ldcs(col4 + i);
+                cc[u][0] = c.x; cc[u][1] = c.y; cc[u][2] = c.z; cc[u][3] = c.w;
+                if (sizeof(T) == 4) {
+                    float4 f = __ldcs(reinterpret_cast<const float4*>(val) + i);
+                    v[u][0] = (T)f.x; v[u][1] = (T)f.y; v[u][2] = (T)f.z; v[u][3] = (T)f.w;
+                } else {
+                    double2 d0 = __ldcs(reinterpret_cast<const double2*>(val) + 2 * i);
+                    double2 d1 = __ldcs(reinterpret_cast<const double2*>(val) + 2 * i + 1);
+                    v[u][0] = (T)d0.x; v[u][1] = (T)d0.y; v[u][2] = (T)d1.x; v[u][3] = (T)d1.y;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UF; u++) {
+            const int64_t i = i0 + (int64_t)u * blockDim.x;
+            if (i < b1) {
+                const int64_t e = i << 2;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (e + k < nnz) {
+                        if (4 * u + k >= 4 * UF - STATS_L2_SLOTS_) {                 // compile-time per unrolled slot
+                            const double x = (double)v[u][k];
+                            atomicAdd(&g_sum[cc[u][k]], x);
+                            if (g_sumsq) atomicAdd(&g_sumsq[cc[u][k]], x * x);
+                        } else {
+                            pair_add(&acc[2 * cc[u][k]], (A)v[u][k]);
+                        }
+                        if (CNT) atomicAdd(&cnt[cc[u][k]], 1u);
+                    }
+                }
             }
         }
     }
@@ -68,94 +126,113 @@ col_stats_flat_kernel(const uint32_t* __restrict__ col, const T* __restrict__ va
     }
 }
 
-// ---- variant 2: column tiles; CTA (tile, row block) touches only its tile's slice of every row ----------
-__device__ __forceinline__ int64_t lower_bound_col(const uint32_t* __restrict__ col, int64_t lo, int64_t hi,
-                                                   uint32_t key) {
-    while (lo < hi) {
-        int64_t mid = (lo + hi) >> 1;
-        if (col[mid] < key) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
-
+// ---- variant 2: column tiles ----------------------------------------------------------------------------------
+// The accumulators of all columns do not fit one CTA's shared memory: every CTA keeps its row block and sweeps it once
+// per column tile.  The column indices of a row ascend, so the entries of tile t are a contiguous run of the row: pass t
+// starts at the position pass t-1 stopped at (row_pos, one u32 per row, written and read by the same warp) and stops at
+// the first batch that reaches the next tile.  Every entry is read from HBM once and no row is searched (the first
+// version gave each (tile, row block) its own CTA and paid two dependent binary searches per row and tile).
 template <typename T, typename A, bool CNT>
 __global__ void __launch_bounds__(1024, 1)
 col_stats_tiled_kernel(const int64_t* __restrict__ ptr, const uint32_t* __restrict__ col, const T* __restrict__ val,
                        int64_t nrows, int ncols, int tile_cols, int n_tiles, double* __restrict__ g_sum,
                        double* __restrict__ g_sumsq, double* __restrict__ g_cnt, const uint32_t* __restrict__ keepbits,
-                       unsigned long long* __restrict__ row_kept) {
+                       unsigned long long* __restrict__ row_kept, uint32_t* __restrict__ row_pos) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     A* acc = reinterpret_cast<A*>(smem_raw);
     unsigned* cnt = reinterpret_cast<unsigned*>(acc + 2 * (size_t)tile_cols);
     unsigned* kb = cnt + (CNT ? tile_cols : 0);        // keep-bitmask of the whole column range (fused compaction count)
-    int tile = blockIdx.x % n_tiles;
-    int rb = blockIdx.x / n_tiles, n_rb = gridDim.x / n_tiles;
-    uint32_t c0 = (uint32_t)tile * tile_cols;
-    uint32_t c1 = c0 + tile_cols < (uint32_t)ncols ? c0 + tile_cols : (uint32_t)ncols;
-    for (int i = threadIdx.x; i < 2 * tile_cols; i += blockDim.x) acc[i] = A(0);
-    if (CNT) for (int i = threadIdx.x; i < tile_cols; i += blockDim.x) cnt[i] = 0u;
     if (keepbits) for (int i = threadIdx.x; i < (ncols + 31) / 32; i += blockDim.x) kb[i] = keepbits[i];
-    __syncthreads();
-    int64_t per = (nrows + n_rb - 1) / n_rb;
-    int64_t r0 = (int64_t)rb * per, r1 = r0 + per < nrows ? r0 + per : nrows;
-    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    for (int64_t r = r0 + warp; r < r1; r += nwarp) {
-        int64_t s = ptr[r], e = ptr[r + 1];
-        if (n_tiles > 1) {
-            int64_t lo = lower_bound_col(col, s, e, c0);
-            e = (c1 >= (uint32_t)ncols) ? e : lower_bound_col(col, lo, e, c1);
-            s = lo;
-        }
-        int kept = 0;
-        for (int64_t p = s + lane; p < e; p += 128) {      // 4 independent loads in flight per lane
-            uint32_t cc[4];
-            T vv[4];
+    const int64_t per = (nrows + gridDim.x - 1) / gridDim.x;
+    const int64_t r0 = (int64_t)blockIdx.x * per, r1 = r0 + per < nrows ? r0 + per : nrows;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    constexpr int U = 8;                                // 8 x 128 B per array in flight per warp
+    for (int tile = 0; tile < n_tiles; tile++) {
+        const uint32_t c0 = (uint32_t)tile * tile_cols;
+        const bool last = tile == n_tiles - 1;
+        const uint32_t c1 = last ? (uint32_t)ncols : c0 + tile_cols;
+        for (int i = threadIdx.x; i < 2 * tile_cols; i += blockDim.x) acc[i] = A(0);
+        if (CNT) for (int i = threadIdx.x; i < tile_cols; i += blockDim.x) cnt[i] = 0u;
+        __syncthreads();
+        for (int64_t r = r0 + warp; r < r1; r += nwarp) {
+            const int64_t s = ptr[r];
+            const uint32_t len = (uint32_t)(ptr[r + 1] - s);
+            const uint32_t start = tile ? row_pos[r] : 0u;
+            const uint32_t* __restrict__ colr = col + s;
+            const T* __restrict__ valr = val + s;
+            int kept = 0, n_in = 0;
+            // one batch of 32*U entries from p0; FULL batches carry no per-load predicate (seven predicate registers
+            // would cap the loads in flight at six), the tail batch clamps its index to the row's last entry.
+            // Returns true when the batch reached the next tile (ascending columns: its last entry is its largest).
+            auto batch = [&](uint32_t p0, auto full_tag) -> bool {
+                constexpr bool FULL = decltype(full_tag)::value;
+                uint32_t cc[U];
+                T vv[U];
+                const uint32_t last_e = len - 1;
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                int64_t q = p + 32 * u;
-                bool ok = q < e;
-                cc[u] = ok ? __ldcs(col + q) : 0u;
-                vv[u] = ok ? __ldcs(val + q) : T(0);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                if (p + 32 * u < e) {
-                    uint32_t c = cc[u] - c0;
-                    A x = (A)vv[u];
-                    smem_add(&acc[2 * c], x);
-                    if (keepbits) {
-                        // masked fit: sum of squares is only needed for the kept columns (total_var,
-                        // pca/sparse_masked/mod.rs:303-307) -> one shared-memory atomic per entry instead of two
-                        const unsigned kbit = (kb[cc[u] >> 5] >> (cc[u] & 31)) & 1u;
-                        kept += kbit;
-                        if (kbit) smem_add(&acc[2 * c + 1], x * x);
-                    } else {
-                        smem_add(&acc[2 * c + 1], x * x);
-                    }
-                    if (CNT) atomicAdd(&cnt[c], 1u);
+                for (int u = 0; u < U; u++) {
+                    uint32_t q = p0 + lane + 32 * u;
+                    if (!FULL) q = q < last_e ? q : last_e;
+                    cc[u] = __ldcs(colr + q);
+                    vv[u] = __ldcs(valr + q);
                 }
-            }
-        }
-        if (keepbits) {
 #pragma unroll
-            for (int o = 16; o; o >>= 1) kept += __shfl_xor_sync(0xFFFFFFFFu, kept, o);
-            if (lane == 0) {
-                if (n_tiles > 1) atomicAdd(&row_kept[r], (unsigned long long)kept);
-                else row_kept[r] = (unsigned long long)kept;
+                for (int u = 0; u < U; u++) {
+                    const bool ok = FULL || p0 + lane + 32 * u < len;
+                    if (ok && (last || cc[u] < c1)) {
+                        const uint32_t c = cc[u] - c0;
+                        const A x = (A)vv[u];
+                        n_in++;
+                        const bool to_l2 = u >= U - STATS_L2_SLOTS_;                 // compile-time per unrolled slot
+                        bool sq = true;
+                        if (keepbits) {
+                            // masked fit: sum of squares is only needed for the kept columns (total_var,
+                            // pca/sparse_masked/mod.rs:303-307)
+                            const unsigned kbit = (kb[cc[u] >> 5] >> (cc[u] & 31)) & 1u;
+                            kept += kbit;
+                            sq = kbit != 0u;
+                        }
+                        if (to_l2) {
+                            atomicAdd(&g_sum[cc[u]], (double)x);
+                            if (sq && g_sumsq) atomicAdd(&g_sumsq[cc[u]], (double)x * (double)x);
+                        } else if (sq) {
+                            pair_add(&acc[2 * c], x);
+                        } else {
+                            smem_add(&acc[2 * c], x);
+                        }
+                        if (CNT) atomicAdd(&cnt[c], 1u);
+                    }
+                }
+                return !last && __any_sync(0xFFFFFFFFu, cc[U - 1] >= c1);
+            };
+            uint32_t p0 = start;
+            bool done = false;
+            for (; !done && p0 + 32 * U <= len; p0 += 32 * U) done = batch(p0, std::true_type{});
+            if (!done && p0 < len) batch(p0, std::false_type{});
+            if (!last) {
+#pragma unroll
+                for (int o = 16; o; o >>= 1) n_in += __shfl_xor_sync(0xFFFFFFFFu, n_in, o);
+                if (lane == 0) row_pos[r] = start + (uint32_t)n_in;
+            }
+            if (keepbits) {
+#pragma unroll
+                for (int o = 16; o; o >>= 1) kept += __shfl_xor_sync(0xFFFFFFFFu, kept, o);
+                if (lane == 0) row_kept[r] = (tile ? row_kept[r] : 0ull) + (unsigned long long)kept;
             }
         }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < (int)(c1 - c0); i += blockDim.x) {
-        A s = acc[2 * i], q = acc[2 * i + 1];
-        if (s != A(0) || q != A(0)) {
-            atomicAdd(&g_sum[c0 + i], (double)s);
-            if (g_sumsq) atomicAdd(&g_sumsq[c0 + i], (double)q);
+        __syncthreads();
+        for (int i = threadIdx.x; i < (int)(c1 - c0); i += blockDim.x) {
+            A s = acc[2 * i], q = acc[2 * i + 1];
+            if (s != A(0) || q != A(0)) {
+                atomicAdd(&g_sum[c0 + i], (double)s);
+                if (g_sumsq) atomicAdd(&g_sumsq[c0 + i], (double)q);
+            }
+            if (CNT) {
+                unsigned n = cnt[i];
+                if (n) atomicAdd(&g_cnt[c0 + i], (double)n);
+            }
         }
-        if (CNT) {
-            unsigned n = cnt[i];
-            if (n) atomicAdd(&g_cnt[c0 + i], (double)n);
-        }
+        __syncthreads();
     }
 }
 
@@ -223,33 +300,58 @@ col_stats_masked_kernel(const int64_t* __restrict__ ptr, const uint32_t* __restr
         const int cap = (int)(((s + len) >> kept_shift) - ks); // slot of this row in the scaled scratch
         uint32_t* __restrict__ kc = kept_col ? kept_col + ks : nullptr;
         T* __restrict__ kv = kept_col ? kept_val + ks : nullptr;
-        for (uint32_t p0 = 0; p0 < len; p0 += 32 * U) {        // warp-uniform trip count (ballots inside)
+        // one batch of 32*U entries (warp-uniform trip count: ballots inside).  FULL batches carry no per-load predicate
+        // (seven predicate registers would cap the loads in flight at six); the tail batch clamps its index to the row's
+        // last entry and lanes past the end add 0 to that entry's column instead of diverging.
+        auto batch = [&](uint32_t p0, auto full_tag) {
+            constexpr bool FULL = decltype(full_tag)::value;
             uint32_t cc[U];
             T vv[U];
-            bool ok[U];
+            const uint32_t last_e = len - 1;
 #pragma unroll
             for (int u = 0; u < U; u++) {
-                const uint32_t q = p0 + lane + 32 * u;
-                ok[u] = q < len;
-                cc[u] = ok[u] ? __ldcs(colr + q) : 0u;
-                vv[u] = ok[u] ? __ldcs(valr + q) : T(0);
+                uint32_t q = p0 + lane + 32 * u;
+                if (!FULL) q = q < last_e ? q : last_e;
+                cc[u] = __ldcs(colr + q);
+                vv[u] = __ldcs(valr + q);
             }
+            // mask lookups of the whole batch first (independent shared-memory reads in flight instead of one exposed
+            // read latency per entry): {kept bit, rank among the kept columns} packed into one register
+#if STATS_MHOIST_
+            unsigned kr[U];
 #pragma unroll
             for (int u = 0; u < U; u++) {
-                const float x = (float)vv[u];
+                const bool ok = FULL || p0 + lane + 32 * u < len;
                 const unsigned b = cc[u] & 31u;
                 const uint2 wp = kb2[cc[u] >> 5];
-                const bool kbit = ok[u] && ((wp.x >> b) & 1u);
+                const unsigned kb1 = ok ? (wp.x >> b) & 1u : 0u;
+                kr[u] = (kb1 << 31) | (wp.y + __popc(wp.x & ((1u << b) - 1u)));
+            }
+#endif
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const bool ok = FULL || p0 + lane + 32 * u < len;
+                const float x = ok ? (float)vv[u] : 0.f;
+#if STATS_MHOIST_
+                const bool kbit = (kr[u] >> 31) != 0u;
+                const unsigned rank = kr[u] & 0x7FFFFFFFu;
+#else
+                const unsigned b = cc[u] & 31u;
+                const uint2 wp = kb2[cc[u] >> 5];
+                const bool kbit = ok && ((wp.x >> b) & 1u);
                 const unsigned rank = wp.y + __popc(wp.x & ((1u << b) - 1u));
+#endif
                 unsigned xi = 0;
+                const bool to_l2 = u >= U - STATS_L2_SLOTS_;                         // compile-time per unrolled slot
                 if (INTSUM) {
                     xi = __float2uint_rz(x);
                     or_bits |= xi;                                                   // any value >= 65536 sets a high bit
                     or_diff |= __float_as_uint(__uint2float_rn(xi)) ^ __float_as_uint(x);   // any non-integer / negative
-                    atomicAdd(&sum_u[cc[u]], xi);
+                    if (!to_l2) atomicAdd(&sum_u[cc[u]], xi);
                 } else {
-                    atomicAdd(&sum[cc[u]], x);
+                    if (!to_l2) atomicAdd(&sum[cc[u]], x);
                 }
+                if (to_l2 && ok) atomicAdd(&g_sum[cc[u]], (double)x);
                 const unsigned bal = __ballot_sync(0xFFFFFFFFu, kbit);
                 if (kbit) {
                     if (INTSUM) {
@@ -269,7 +371,10 @@ col_stats_masked_kernel(const int64_t* __restrict__ ptr, const uint32_t* __restr
                 }
                 kept += __popc(bal);
             }
-        }
+        };
+        uint32_t p0 = 0;
+        for (; p0 + 32 * U <= len; p0 += 32 * U) batch(p0, std::true_type{});
+        if (p0 < len) batch(p0, std::false_type{});
         if (lane == 0) {
             row_kept[r] = (unsigned long long)kept;
             if (kept_col && kept > cap) atomicOr(&flags[0], 1);
@@ -360,15 +465,13 @@ static void col_stats_launch(salg_ctx* ctx, const salg_csr* c, double* d_sum, do
         int tile_cols = (int)((kMaxSmem - kb_bytes) / per_col);
         int n_tiles = (int)ceil_div(ncols, tile_cols);
         tile_cols = (int)ceil_div(ncols, n_tiles);  // balance the tiles
-        int n_rb = ctx->sm_count / n_tiles;
-        if (n_rb < 1) n_rb = 1;
-        if ((int64_t)n_rb > c->nrows) n_rb = (int)(c->nrows > 0 ? c->nrows : 1);
+        int grid = (int)(c->nrows < ctx->sm_count ? (c->nrows > 0 ? c->nrows : 1) : ctx->sm_count);
         auto k = col_stats_tiled_kernel<T, A, CNT>;
         set_max_dyn_smem(k, (int)((int)kMaxSmem));
-        if (row_kept && n_tiles > 1) SALG_CUDA(cudaMemsetAsync(row_kept, 0, (size_t)(c->nrows + 1) * 8, st));
-        k<<<n_rb * n_tiles, 1024, per_col * (size_t)tile_cols + kb_bytes, st>>>(
+        DevBuf<uint32_t> row_pos(n_tiles > 1 ? (size_t)c->nrows : 0, st);   // where the next tile's pass resumes in each row
+        k<<<grid, 1024, per_col * (size_t)tile_cols + kb_bytes, st>>>(
             c->row_ptr, c->col, (const T*)c->val, c->nrows, ncols, tile_cols, n_tiles, d_sum, d_sumsq, d_cnt, keepbits,
-            (unsigned long long*)row_kept);
+            (unsigned long long*)row_kept, row_pos.get());
         ctx->n_launch++;
     }
     SALG_CUDA(cudaGetLastError());
@@ -423,25 +526,60 @@ bool col_stats_can_fuse_compaction(const salg_csr* c, int64_t n_kept) {
 
 // ---- sum_row ----------------------------------------------------------------------------------------------
 // per-row sum and sum of squares (the CSC twins: a column of A is a row of the stored CSR of A^T)
+// One warp per row, kSumU independent 128 B loads in flight per lane (one load per trip left the pass latency bound).
+constexpr int kSumU = 16;
+
+// Whole batches carry no per-load predicate (ptxas has seven predicate registers: predicated loads are issued six at
+// a time, then wait); the tail batch clamps its index to the last entry of the row and zeroes the value afterwards.
+template <typename T, bool SQ>
+__device__ __forceinline__ void warp_row_sums(const T* __restrict__ vr, uint32_t len, int lane, double& a, double& q) {
+    constexpr int RU = sizeof(T) == 4 ? kSumU : kSumU / 2;
+    a = 0.0;
+    q = 0.0;
+    uint32_t p0 = 0;
+    for (; p0 + 32 * RU <= len; p0 += 32 * RU) {
+        T v[RU];
+#pragma unroll
+        for (int u = 0; u < RU; u++) v[u] = __ldcs(vr + p0 + lane + 32 * u);
+#pragma unroll
+        for (int u = 0; u < RU; u++) {
+            const double x = (double)v[u];
+            a += x;
+            if (SQ) q = fma(x, x, q);
+        }
+    }
+    if (p0 < len) {
+        T v[RU];
+        const uint32_t last = len - 1;
+#pragma unroll
+        for (int u = 0; u < RU; u++) {
+            const uint32_t i = p0 + lane + 32 * u;
+            v[u] = __ldcs(vr + (i < last ? i : last));
+        }
+#pragma unroll
+        for (int u = 0; u < RU; u++) {
+            const double x = p0 + lane + 32 * u < len ? (double)v[u] : 0.0;
+            a += x;
+            if (SQ) q = fma(x, x, q);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
+        if (SQ) q += __shfl_xor_sync(0xFFFFFFFFu, q, o);
+    }
+}
+
 template <typename T>
-__global__ void sum_row_sq_kernel(const int64_t* __restrict__ ptr, const T* __restrict__ val, int64_t nrows,
+__global__ void __launch_bounds__(256, 4) sum_row_sq_kernel(const int64_t* __restrict__ ptr, const T* __restrict__ val, int64_t nrows,
                                   T* __restrict__ out, T* __restrict__ out_sq) {
     int lane = threadIdx.x & 31;
     int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t r = w; r < nrows; r += nw) {
-        int64_t s = ptr[r], e = ptr[r + 1];
-        double a = 0.0, q = 0.0;
-        for (int64_t p = s + lane; p < e; p += 32) {
-            const double v = (double)__ldcs(val + p);
-            a += v;
-            q = fma(v, v, q);
-        }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
-            q += __shfl_xor_sync(0xFFFFFFFFu, q, o);
-        }
+        const int64_t s = ptr[r];
+        double a, q;
+        warp_row_sums<T, true>(val + s, (uint32_t)(ptr[r + 1] - s), lane, a, q);
         if (lane == 0) {
             if (out) out[r] = (T)a;
             if (out_sq) out_sq[r] = (T)q;
@@ -450,17 +588,15 @@ __global__ void sum_row_sq_kernel(const int64_t* __restrict__ ptr, const T* __re
 }
 
 template <typename T>
-__global__ void sum_row_kernel(const int64_t* __restrict__ ptr, const T* __restrict__ val, int64_t nrows,
+__global__ void __launch_bounds__(256, 4) sum_row_kernel(const int64_t* __restrict__ ptr, const T* __restrict__ val, int64_t nrows,
                                T* __restrict__ out) {
     int lane = threadIdx.x & 31;
     int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t r = w; r < nrows; r += nw) {
-        int64_t s = ptr[r], e = ptr[r + 1];
-        double a = 0.0;
-        for (int64_t p = s + lane; p < e; p += 32) a += (double)__ldcs(val + p);
-#pragma unroll
-        for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
+        const int64_t s = ptr[r];
+        double a, q;
+        warp_row_sums<T, false>(val + s, (uint32_t)(ptr[r + 1] - s), lane, a, q);
         if (lane == 0) out[r] = (T)a;
     }
 }
