@@ -287,7 +287,7 @@ __global__ void tc_tile_ptr_kernel(const uint32_t* __restrict__ keys_sorted, int
 constexpr int TC_BIN_THREADS = 512;
 constexpr int TC_BIN_MAX_CB = 4096;
 template <typename T>
-__global__ void __launch_bounds__(TC_BIN_THREADS)
+__global__ void __launch_bounds__(TC_BIN_THREADS, 2)
 tc_bin_kernel(const int64_t* __restrict__ in_ptr, int in_shift, const int64_t* __restrict__ ptr, const uint32_t* __restrict__ col,
               const T* __restrict__ val, int64_t nrows,
               int64_t nnz, int n_rb, int n_cb, uint2* __restrict__ entries, int64_t* __restrict__ tile_ptr,
@@ -309,15 +309,43 @@ tc_bin_kernel(const int64_t* __restrict__ in_ptr, int in_shift, const int64_t* _
         __syncthreads();
         for (int i = tid; i < n_cb; i += TC_BIN_THREADS) hist[i] = 0;
         __syncthreads();
+        // The warp's rows (r0 + warp + NW i): start and length fetched once by lanes i, broadcast per row — the sweeps
+        // below never wait on a pointer load.  Each sweep reads a row in batches of BU x 32 entries with every load issued
+        // before the first use (indices clamped to the row's last entry: no per-load predicates); one load per trip left
+        // this kernel latency bound (1.29 ms for the cfg3 operator).
+        constexpr int BU = 8;
+        constexpr int RPW = TC_RB / NW;                        // rows per warp
+        int64_t my_s = 0;
+        uint32_t my_len = 0;
+        if (lane < RPW) {
+            const int64_t r = r0 + warp + (int64_t)NW * lane;
+            if (r < r1) {
+                const int64_t a0 = ptr[r];
+                my_s = in_ptr[r] >> in_shift;
+                my_len = (uint32_t)(ptr[r + 1] - a0);
+            }
+        }
         // sweep 1: column-block histogram (columns ascend inside a row: equal blocks sit in adjacent lanes)
-        for (int64_t r = r0 + warp; r < r1; r += NW) {
-            const int64_t s = in_ptr[r] >> in_shift, e = s + (ptr[r + 1] - ptr[r]);
-            for (int64_t p0 = s; p0 < e; p0 += 32) {
-                const int64_t p = p0 + lane;
-                const bool ok = p < e;
-                const unsigned cb = ok ? col[p] / TC_CB : 0xFFFFFFFFu;
-                const unsigned peers = __match_any_sync(0xFFFFFFFFu, cb);
-                if (ok && lane == __ffs(peers) - 1) atomicAdd(&hist[cb], (unsigned)__popc(peers));
+        for (int i = 0; i < RPW; i++) {
+            const int64_t s = __shfl_sync(0xFFFFFFFFu, my_s, i);
+            const uint32_t len = __shfl_sync(0xFFFFFFFFu, my_len, i);
+            const uint32_t* __restrict__ cr = col + s;
+            const uint32_t last = len - 1;
+            for (uint32_t p0 = 0; p0 < len; p0 += 32 * BU) {
+                uint32_t c[BU];
+#pragma unroll
+                for (int u = 0; u < BU; u++) {
+                    const uint32_t q = p0 + lane + 32 * u;
+                    c[u] = cr[q < last ? q : last];
+                }
+#pragma unroll
+                for (int u = 0; u < BU; u++) {
+                    if (p0 + 32 * u >= len) break;            // warp-uniform
+                    const bool ok = p0 + lane + 32 * u < len;
+                    const unsigned cb = ok ? c[u] / TC_CB : 0xFFFFFFFFu;
+                    const unsigned peers = __match_any_sync(0xFFFFFFFFu, cb);
+                    if (ok && lane == __ffs(peers) - 1) atomicAdd(&hist[cb], (unsigned)__popc(peers));
+                }
             }
         }
         __syncthreads();
@@ -348,29 +376,45 @@ tc_bin_kernel(const int64_t* __restrict__ in_ptr, int in_shift, const int64_t* _
         bool bad = false;
         float amax = 0.f;
         const unsigned rb1 = (unsigned)rb & 1u;
-        for (int64_t r = r0 + warp; r < r1; r += NW) {
-            const int64_t s = in_ptr[r] >> in_shift, e = s + (ptr[r + 1] - ptr[r]);
-            const unsigned lr = (unsigned)(r - r0);
-            for (int64_t p0 = s; p0 < e; p0 += 32) {
-                const int64_t p = p0 + lane;
-                const bool ok = p < e;
-                const unsigned c = ok ? col[p] : 0u;
-                const unsigned cb = ok ? c / TC_CB : 0xFFFFFFFFu;
-                const unsigned peers = __match_any_sync(0xFFFFFFFFu, cb);
-                const int leader = __ffs(peers) - 1;
-                unsigned start = 0;
-                if (ok && lane == leader) start = atomicAdd(&hist[cb], (unsigned)__popc(peers));
-                start = __shfl_sync(0xFFFFFFFFu, start, leader);
-                if (ok) {
-                    const float v = (float)val[p];
-                    const unsigned lc = c % TC_CB;
-                    // positions inside the 32 KB sparse-operand buffers of the two kernels (see tc_scatter_role)
-                    const uint32_t off_ax = canon_off(lr + 128u * rb1, lc, 4096u) >> 1;
-                    const uint32_t off_aty = canon_off(lc + 64u * (cb & 1u), lr, 2048u) >> 1;
-                    entries[base + start + __popc(peers & ((1u << lane) - 1u))] =
-                        make_uint2(off_ax | (off_aty << 14), __float_as_uint(v));
-                    bad |= (__half2float(__float2half_rn(v)) != v);
-                    amax = fmaxf(amax, fabsf(v));
+        for (int i = 0; i < RPW; i++) {
+            const int64_t s = __shfl_sync(0xFFFFFFFFu, my_s, i);
+            const uint32_t len = __shfl_sync(0xFFFFFFFFu, my_len, i);
+            const uint32_t* __restrict__ cr = col + s;
+            const T* __restrict__ vr = val + s;
+            const uint32_t last = len - 1;
+            const unsigned lr = (unsigned)(warp + NW * i);
+            for (uint32_t p0 = 0; p0 < len; p0 += 32 * BU) {
+                uint32_t cc[BU];
+                T vv[BU];
+#pragma unroll
+                for (int u = 0; u < BU; u++) {
+                    uint32_t q = p0 + lane + 32 * u;
+                    q = q < last ? q : last;
+                    cc[u] = cr[q];
+                    vv[u] = vr[q];
+                }
+#pragma unroll
+                for (int u = 0; u < BU; u++) {
+                    if (p0 + 32 * u >= len) break;            // warp-uniform
+                    const bool ok = p0 + lane + 32 * u < len;
+                    const unsigned c = cc[u];
+                    const unsigned cb = ok ? c / TC_CB : 0xFFFFFFFFu;
+                    const unsigned peers = __match_any_sync(0xFFFFFFFFu, cb);
+                    const int leader = __ffs(peers) - 1;
+                    unsigned start = 0;
+                    if (ok && lane == leader) start = atomicAdd(&hist[cb], (unsigned)__popc(peers));
+                    start = __shfl_sync(0xFFFFFFFFu, start, leader);
+                    if (ok) {
+                        const float v = (float)vv[u];
+                        const unsigned lc = c % TC_CB;
+                        // positions inside the 32 KB sparse-operand buffers of the two kernels (see tc_scatter_role)
+                        const uint32_t off_ax = canon_off(lr + 128u * rb1, lc, 4096u) >> 1;
+                        const uint32_t off_aty = canon_off(lc + 64u * (cb & 1u), lr, 2048u) >> 1;
+                        entries[base + start + __popc(peers & ((1u << lane) - 1u))] =
+                            make_uint2(off_ax | (off_aty << 14), __float_as_uint(v));
+                        bad |= (__half2float(__float2half_rn(v)) != v);
+                        amax = fmaxf(amax, fabsf(v));
+                    }
                 }
             }
         }
