@@ -50,6 +50,10 @@ template <> struct Abi<float> {
     static constexpr auto sum_col = salg_sum_col_f32;
     static constexpr auto sum_row = salg_sum_row_f32;
     static constexpr auto normalize = salg_normalize_f32;
+    static constexpr auto csc_upload = salg_csc_upload_f32;
+    static constexpr auto csc_sum_col = salg_csc_sum_col_f32;
+    static constexpr auto csc_sum_row = salg_csc_sum_row_f32;
+    static constexpr auto csc_normalize = salg_csc_normalize_f32;
     static constexpr auto pca_fit = salg_pca_fit_f32;
     static constexpr auto pca_components = salg_pca_components_f32;
     static constexpr auto pca_transform = salg_pca_transform_f32;
@@ -61,6 +65,10 @@ template <> struct Abi<double> {
     static constexpr auto sum_col = salg_sum_col_f64;
     static constexpr auto sum_row = salg_sum_row_f64;
     static constexpr auto normalize = salg_normalize_f64;
+    static constexpr auto csc_upload = salg_csc_upload_f64;
+    static constexpr auto csc_sum_col = salg_csc_sum_col_f64;
+    static constexpr auto csc_sum_row = salg_csc_sum_row_f64;
+    static constexpr auto csc_normalize = salg_csc_normalize_f64;
     static constexpr auto pca_fit = salg_pca_fit_f64;
     static constexpr auto pca_components = salg_pca_components_f64;
     static constexpr auto pca_transform = salg_pca_transform_f64;
@@ -224,6 +232,95 @@ public:
 
 private:
     void pull_values() {      // the in-place operations ran on the device copy: bring the values back (&mut self)
+        detail::check(detail::Abi<T>::csr_download(ctx().handle(), dev_, nullptr, nullptr, val_.data()));
+    }
+    std::size_t nrows_ = 0, ncols_ = 0;
+    std::vector<std::uint64_t> off_, idx_;
+    std::vector<T> val_;
+    Context* ctx_ = nullptr;
+    mutable salg_csr* dev_ = nullptr;
+};
+
+// nalgebra_sparse::CscMatrix<T>: usize column offsets [ncols + 1], usize row indices [nnz] strictly increasing inside a
+// column, values T [nnz] — the CSC twins of the traits.  The device keeps it as the CSR of A^T.
+template <typename T>
+class CscMatrix {
+    static_assert(std::is_same<T, float>::value || std::is_same<T, double>::value, "T is f32 or f64");
+
+public:
+    CscMatrix(std::size_t nrows, std::size_t ncols, std::vector<std::uint64_t> col_offsets,
+              std::vector<std::uint64_t> row_indices, std::vector<T> values, Context* ctx = nullptr)
+        : nrows_(nrows), ncols_(ncols), off_(std::move(col_offsets)), idx_(std::move(row_indices)), val_(std::move(values)),
+          ctx_(ctx) {
+        if (off_.size() != ncols_ + 1) throw Error(SALG_ERR_BAD_ARG, "col_offsets must have ncols + 1 entries");
+        if (idx_.size() != val_.size()) throw Error(SALG_ERR_BAD_ARG, "row_indices and values differ in length");
+    }
+    ~CscMatrix() { drop_device(); }
+    CscMatrix(const CscMatrix&) = delete;
+    CscMatrix& operator=(const CscMatrix&) = delete;
+    CscMatrix(CscMatrix&& o) noexcept
+        : nrows_(o.nrows_), ncols_(o.ncols_), off_(std::move(o.off_)), idx_(std::move(o.idx_)), val_(std::move(o.val_)),
+          ctx_(o.ctx_), dev_(o.dev_) {
+        o.dev_ = nullptr;
+    }
+
+    std::size_t nrows() const { return nrows_; }
+    std::size_t ncols() const { return ncols_; }
+    std::size_t nnz() const { return val_.size(); }
+    const std::vector<std::uint64_t>& col_offsets() const { return off_; }
+    const std::vector<std::uint64_t>& row_indices() const { return idx_; }
+    const std::vector<T>& values() const { return val_; }
+    std::vector<T>& values_mut() {
+        drop_device();
+        return val_;
+    }
+
+    // MatrixSum for CscMatrix: sum_col (src/sparse/csc.rs:157-197), sum_col_squared (:323-335), sum_row (:199-220)
+    std::vector<T> sum_col() const {
+        std::vector<T> s(ncols_);
+        detail::check(detail::Abi<T>::csc_sum_col(ctx().handle(), device(), s.data(), nullptr));
+        return s;
+    }
+    std::vector<T> sum_col_squared() const {
+        std::vector<T> q(ncols_);
+        detail::check(detail::Abi<T>::csc_sum_col(ctx().handle(), device(), nullptr, q.data()));
+        return q;
+    }
+    std::vector<T> sum_row() const {
+        std::vector<T> s(nrows_);
+        detail::check(detail::Abi<T>::csc_sum_row(ctx().handle(), device(), s.data()));
+        return s;
+    }
+    // Normalize::normalize for CscMatrix (src/sparse/csc.rs:680-735): ROW indexes `sums` by row_indices, COLUMN by column
+    void normalize(const std::vector<T>& sums, T target, Direction direction) {
+        detail::check(detail::Abi<T>::csc_normalize(ctx().handle(), device(), sums.data(), (std::int64_t)sums.size(), target,
+                                                    (int)direction));
+        pull_values();
+    }
+    // Log1P::log1p_normalize for CscMatrix (src/sparse/csc.rs:737-746)
+    void log1p_normalize() {
+        detail::check(salg_log1p(ctx().handle(), device()));
+        pull_values();
+    }
+
+    Context& ctx() const { return ctx_ ? *ctx_ : Context::default_context(); }
+    salg_csr* device() const {
+        if (!dev_) {
+            detail::check(detail::Abi<T>::csc_upload(ctx().handle(), (std::int64_t)nrows_, (std::int64_t)ncols_,
+                                                     (std::int64_t)val_.size(), off_.data(), idx_.data(), val_.data(),
+                                                     &dev_));
+        }
+        return dev_;
+    }
+    void drop_device() const {
+        if (dev_) {
+            salg_csr_free(dev_);
+            dev_ = nullptr;
+        }
+    }
+
+private:
+    void pull_values() {
         detail::check(detail::Abi<T>::csr_download(ctx().handle(), dev_, nullptr, nullptr, val_.data()));
     }
     std::size_t nrows_ = 0, ncols_ = 0;

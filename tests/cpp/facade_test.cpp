@@ -1,6 +1,7 @@
 // facade_test.cpp — the reference's own tests for the hot path, written against the C++ facade
 // (include/single_algebra.hpp) exactly as the Rust tests are written against the crate:
 //   test_csr_normalize                      src/sparse/csr.rs:1514-1550   (KAT-N1)
+//   test_matrix_sum / test_csc_normalization / test_zero_elements   src/sparse/csc.rs:1123-1152, 1256-1301, 1303-1314 (KAT-S1, N2, L1)
 //   test_random_matrix_sparse_svd_comp_random  src/dimred/pca/sparse/mod.rs:540-562 (asserts is_ok(); here at a reduced
 //                                           size by default, `--full` runs the reference's 10M x 2500 at 1 %)
 // plus the error behaviour of the masked type (pca/sparse_masked/mod.rs:258-262, 440-444) and plain-loop checks of
@@ -97,6 +98,49 @@ static void test_sums_and_log1p(const char* name) {
     double want0 = 100.0 + a.values()[1] + a.values()[2];
     CHECK(std::fabs(again[0] - want0) <= 1e-5 * want0, "%s sum_row after values_mut = %g, want %g", name, (double)again[0], want0);
     std::printf("ok test_sums_and_log1p<%s>\n", name);
+}
+
+// CooMatrix -> CscMatrix for small triplet lists (any order)
+static CscMatrix<double> csc_from_triplets(std::size_t nrows, std::size_t ncols, const std::vector<std::size_t>& ri,
+                                           const std::vector<std::size_t>& ci, const std::vector<double>& v) {
+    std::vector<std::uint64_t> off(ncols + 1, 0), idx;
+    std::vector<double> val;
+    for (std::size_t c = 0; c < ncols; c++) {
+        for (std::size_t r = 0; r < nrows; r++)
+            for (std::size_t i = 0; i < v.size(); i++)
+                if (ci[i] == c && ri[i] == r) {
+                    idx.push_back(r);
+                    val.push_back(v[i]);
+                }
+        off[c + 1] = idx.size();
+    }
+    return CscMatrix<double>(nrows, ncols, off, idx, val);
+}
+
+// src/sparse/csc.rs:1123-1152 (matrix of :1071-1093), :1256-1301, :1303-1314
+static void test_csc_twins() {
+    auto m = csc_from_triplets(3, 3, {0, 2, 1, 0, 2}, {0, 0, 1, 2, 2}, {1.0, 4.0, 3.0, 2.0, 5.0});
+    CHECK((m.sum_col() == std::vector<double>{5.0, 3.0, 7.0}), "Column sums should match");
+    CHECK((m.sum_row() == std::vector<double>{3.0, 3.0, 9.0}), "Row sums should match");
+    CHECK((m.sum_col_squared() == std::vector<double>{17.0, 9.0, 29.0}), "Column sums of squares");
+    const std::vector<std::size_t> ri{0, 1, 2, 0, 2}, ci{0, 1, 0, 2, 2};
+    const std::vector<double> v{2.0, 4.0, 1.0, 3.0, 5.0};
+    auto csc = csc_from_triplets(3, 3, ri, ci, v);
+    csc.normalize(std::vector<double>{3.0, 4.0, 8.0}, 1.0, Direction::COLUMN);
+    for (std::size_t c = 0; c < 3; c++) {
+        double s = 0;
+        for (auto j = csc.col_offsets()[c]; j < csc.col_offsets()[c + 1]; j++) s += csc.values()[j];
+        CHECK(std::fabs(s - 1.0) < 1e-10, "column %zu sums to %g after COLUMN normalisation", c, s);
+    }
+    auto csc2 = csc_from_triplets(3, 3, ri, ci, v);
+    csc2.normalize(std::vector<double>{5.0, 4.0, 6.0}, 1.0, Direction::ROW);
+    double rs[3] = {0, 0, 0};
+    for (std::size_t j = 0; j < csc2.nnz(); j++) rs[csc2.row_indices()[j]] += csc2.values()[j];
+    for (int r = 0; r < 3; r++) CHECK(std::fabs(rs[r] - 1.0) < 1e-10, "row %d sums to %g after ROW normalisation", r, rs[r]);
+    auto z = csc_from_triplets(2, 2, {0, 1}, {0, 1}, {0.0, 0.0});
+    z.log1p_normalize();
+    for (double x : z.values()) CHECK(std::fabs(x) < 1e-10, "ln(1 + 0) = %g", x);
+    std::printf("ok test_csc_twins\n");
 }
 
 // create_sparse_matrix of the reference's test module (pca/sparse/mod.rs:493-537): uniform random positions without
@@ -241,6 +285,7 @@ int main(int argc, char** argv) {
         test_csr_normalize();
         test_sums_and_log1p<float>("f32");
         test_sums_and_log1p<double>("f64");
+        test_csc_twins();
         test_random_matrix_sparse_svd_comp_random(full);
         test_masked();
     } catch (const Error& e) {

@@ -38,6 +38,6 @@ def test_reference_tests_through_the_cpp_facade():
     exe = build_facade_test()
     r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "all facade tests passed" in r.stdout, (r.stdout[-3000:], r.stderr[-2000:])
-    for name in ("test_csr_normalize", "test_sums_and_log1p<f32>", "test_sums_and_log1p<f64>",
+    for name in ("test_csr_normalize", "test_sums_and_log1p<f32>", "test_sums_and_log1p<f64>", "test_csc_twins",
                  "test_random_matrix_sparse_svd_comp_random", "test_masked"):
         assert "ok " + name in r.stdout, r.stdout
