@@ -179,10 +179,13 @@ def run_ours(args, wl):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
+    numa_cpus = 0
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group(backend="cpu:gloo,cuda:nccl")
+        if not os.environ.get("SALG_NO_NUMA_BIND"):
+            numa_cpus = s.dist.bind_to_gpu_numa_node(local)     # before any pinned allocation (first touch)
     if s.device_count() == 0:
         raise RuntimeError("bench.py needs a CUDA device: libsalg_b200 has no CPU fallback")
     ctx = s.dist.init_context_from_env()
@@ -357,7 +360,8 @@ def run_ours(args, wl):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["name"], "rows": wl["nrows"], "cols": wl["ncols"], "nnz_per_gpu_rank0": dev.nnz,
                        "parallelism": f"rows sharded over {world} GPU(s)", "l2": "inputs larger than L2; no flush needed",
-                       "omega": "host-generated PCG64(42) standard normal"},
+                       "omega": "host-generated PCG64(42) standard normal",
+                       "host_cpus_bound_to_gpu_numa_node_rank0": numa_cpus},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "kernel_classes": classes, "cpu_baseline": cpu,
         }

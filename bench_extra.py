@@ -82,6 +82,10 @@ def cfg4(ctx):
     spec = s.synth.make_spec(nrows, ncols, density=0.07, seed=42)
     d = s.synth_device(spec, dtype=np.float64, ctx=ctx)
     pca = s.SparsePCABuilder().n_components(50).svd_method(s.SVDMethod.Lanczos).build()
+    ctx.sync()
+    t0 = time.perf_counter()
+    pca.fit(d)                 # cold: the transposed copy's buffers and the Krylov bases grow the memory pool
+    dt_cold = time.perf_counter() - t0
     ctx.prof_reset(); ctx.prof_enable(True)
     ctx.sync()
     t0 = time.perf_counter()
@@ -90,7 +94,8 @@ def cfg4(ctx):
     ctx.prof_enable(False)
     pr = ctx.prof()
     sp = pr.get("spmv")
-    res = {"config": "cfg4 SparsePCA f64 Lanczos 250k x 20k @7%, k=50", "fit_seconds": dt, "nnz": d.nnz,
+    res = {"config": "cfg4 SparsePCA f64 Lanczos 250k x 20k @7%, k=50", "fit_seconds": dt, "first_fit_seconds_cold_pool": dt_cold,
+           "nnz": d.nnz,
            "numeric_flags": pca.numeric_flags()}
     if sp:
         res.update({"spmv_launches": sp[1], "spmv_ms_avg": sp[0] / sp[1], "spmv_achieved_gbs": sp[2] / sp[0] / 1e6,

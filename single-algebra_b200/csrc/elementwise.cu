@@ -198,34 +198,34 @@ __global__ void __launch_bounds__(256) preprocess_row_kernel(const int64_t* __re
                 const uint32_t q = lane + 32 * u;
                 T x = v[u];
                 if (scaled) x = (T)(x * sc);
-                if (q < len) vr[q] = ln_1p_two_step(x);
+                if (q < len) __stcs(vr + q, ln_1p_two_step(x));
             }
             continue;
         }
-        // second touch: L1 / L2, the row was just read
+        // second touch: served by L2 (the row was just read).  Last-use loads and streaming stores keep the rows that
+        // are between their two touches resident instead of the lines nobody will read again.
         for (p0 = 0; p0 + 32 * RU <= len; p0 += 32 * RU) {
 #pragma unroll
-            for (int u = 0; u < RU; u++) v[u] = vr[p0 + lane + 32 * u];
+            for (int u = 0; u < RU; u++) v[u] = __ldlu(vr + p0 + lane + 32 * u);
 #pragma unroll
             for (int u = 0; u < RU; u++) {
                 T x = v[u];
                 if (scaled) x = (T)(x * sc);
-                vr[p0 + lane + 32 * u] = ln_1p_two_step(x);
+                __stcs(vr + p0 + lane + 32 * u, ln_1p_two_step(x));
             }
         }
         if (p0 < len) {
 #pragma unroll
             for (int u = 0; u < RU; u++) {
                 const uint32_t q = p0 + lane + 32 * u;
-                v[u] = vr[q < last ? q : last];
+                v[u] = q < len ? __ldlu(vr + q) : T(0);    // (no clamped re-read of an entry another lane is updating)
             }
-            __syncwarp();                                  // every clamped read of the last entry precedes its update
 #pragma unroll
             for (int u = 0; u < RU; u++) {
                 const uint32_t q = p0 + lane + 32 * u;
                 T x = v[u];
                 if (scaled) x = (T)(x * sc);
-                if (q < len) vr[q] = ln_1p_two_step(x);
+                if (q < len) __stcs(vr + q, ln_1p_two_step(x));
             }
         }
     }
@@ -299,7 +299,8 @@ static void preprocess_api(salg_ctx* ctx, salg_csr* c, T target, T* col_sum, T* 
     cudaStream_t st = ctx->stream;
     if (c->nrows && c->nnz) {
         ProfScope ps(ctx, PROF_ELEMENTWISE, 2.0 * (double)c->nnz * sizeof(T) + (double)(c->nrows + 1) * 8);
-        int64_t want = ceil_div(c->nrows * 32, 256), cap = (int64_t)ctx->sm_count * 4;
+        static const int ctas_per_sm = getenv("SALG_PRE_CTAS") ? atoi(getenv("SALG_PRE_CTAS")) : 4;
+        int64_t want = ceil_div(c->nrows * 32, 256), cap = (int64_t)ctx->sm_count * ctas_per_sm;
         preprocess_row_kernel<T><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(c->row_ptr, (T*)c->val, c->nrows,
                                                                                       target);
         ctx->n_launch++;

@@ -58,6 +58,23 @@ def broadcast_unique_id(make_id, rank, world):
     return bytes(buf.numpy().tobytes())
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Multi-rank runs: pin this process (and with it the first-touch placement of the pinned host buffers it allocates
+    afterwards) to the CPUs NVML reports as closest to its GPU, so that the 8 concurrent host->device uploads of a
+    row-sharded fit do not cross the socket interconnect.  Best effort: returns the CPU count bound to, or 0."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return 0
+
+
 def init_context_from_env():
     """Context for this process under torchrun (RANK / LOCAL_RANK / WORLD_SIZE); torch.distributed must
     already be initialised when WORLD_SIZE > 1."""
