@@ -177,3 +177,46 @@ def test_csc_twins_match_csr(salg, ctx, dtype):
         Bc = sp.csc_matrix((c2.values, c2.row_indices.astype(np.int64), c2.col_offsets.astype(np.int64)), shape=A.shape)
         Br = sp.csr_matrix((r2.values, r2.col_indices.astype(np.int64), r2.row_offsets.astype(np.int64)), shape=A.shape)
         assert abs(Bc - Br).max() == 0.0                 # same arithmetic on both layouts: bit-identical values
+
+
+# ---- batch boundaries of the row streams (whole batches of 32 x U entries without per-load predicates, clamped tail batch) ------
+def _ragged(lengths, ncols, dtype, seed):
+    rng = np.random.default_rng(seed)
+    indptr = np.zeros(len(lengths) + 1, np.int64)
+    indptr[1:] = np.cumsum(lengths)
+    idx = np.concatenate([np.sort(rng.choice(ncols, n, replace=False)) for n in lengths] or [np.zeros(0, np.int64)])
+    val = (rng.integers(1, 9, indptr[-1]) + rng.random(indptr[-1])).astype(dtype)
+    return sp.csr_matrix((val, idx.astype(np.int64), indptr), shape=(len(lengths), ncols))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("ncols", [6000, 70000])
+def test_row_streams_at_batch_boundaries(salg, ctx, dtype, ncols):
+    """Row lengths around every batch size in use (32 x 8 = 256, 32 x 16 = 512, 256-thread CTAs x 8 = 2048) plus empty and
+    one-entry rows; 70000 columns puts the column statistics on the tiled kernel with whole batches that straddle tile
+    borders."""
+    lengths = [0, 1, 2, 31, 32, 33, 255, 256, 257, 0, 511, 512, 513, 767, 768, 1023, 1024, 1025, 2047, 2048, 2049, 4100, 5999, 0]
+    A = _ragged(lengths, ncols, dtype, seed=ncols)
+    m = salg.CsrMatrix.from_scipy(A, ctx)
+    d = m.to_device()
+    s, q = d.sum_col_and_squared()
+    assert np.allclose(s, O.sum_col(A.indptr, A.indices, A.data, ncols), rtol=TOL[dtype], atol=0)
+    assert np.allclose(q, O.sum_col_squared(A.indptr, A.indices, A.data, ncols), rtol=TOL[dtype], atol=0)
+    rs = d.sum_row()
+    assert np.allclose(rs, O.sum_row(A.indptr, A.indices, A.data, A.shape[0]), rtol=TOL[dtype], atol=0)
+    # transposed SpMV-style check of the Lanczos product kernels is covered by test_gpu_pca; here the in-place streams
+    ref = O.normalize(A.indptr, A.indices, A.data, rs, dtype(1e4), O.ROW)
+    m.normalize(rs, dtype(1e4), salg.Direction.ROW)
+    assert np.allclose(m.values, ref, rtol=(2e-6 if dtype == np.float32 else 1e-14), atol=0)
+    m.log1p_normalize()
+    assert np.allclose(m.values, O.log1p_normalize(ref), rtol=(1e-6 if dtype == np.float32 else 1e-14), atol=0)
+    # fused chain on a fresh copy
+    d2 = salg.CsrMatrix.from_scipy(A, ctx).to_device()
+    d2.preprocess(1e4)
+    assert np.allclose(d2.download_values(), O.log1p_normalize(ref), rtol=(2e-6 if dtype == np.float32 else 1e-14), atol=0)
+    # column normalisation (flat kernel, 4 entries per thread, tail of < 4 entries)
+    m3 = salg.CsrMatrix.from_scipy(A, ctx)
+    cs = m3.sum_col()
+    m3.normalize(cs, dtype(1.0), salg.Direction.COLUMN)
+    ref3 = O.normalize(A.indptr, A.indices, A.data, cs, dtype(1.0), O.COLUMN)
+    assert np.allclose(m3.values, ref3, rtol=(2e-6 if dtype == np.float32 else 1e-14), atol=0)
