@@ -300,3 +300,29 @@ def test_f32_power_iteration_counts(salg, ctx, q, p_over):
     # sketch; their angle is governed by the f32 rounding of tiny gaps), so compare the leading half there
     lead = k if q > 0 else k // 2
     assert O.largest_principal_angle(pca.components_[:lead], ref.components[:lead]) < (ANGLE_TOL if q > 0 else 5e-3)
+
+
+@pytest.mark.parametrize("dtype,ncols", [(np.float64, 20000), (np.float32, 50000)])
+def test_masked_fit_through_the_column_tiled_statistics(salg, ctx, dtype, ncols):
+    """Wide masked fits whose accumulators do not fit one shared-memory tile (f64 beyond ~12.7k columns, f32 beyond ~45k):
+    the column-tiled statistics kernel sweeps each row block once per tile and carries the kept-entry count of a row across
+    the tiles; the compaction built from those counts feeds the fit, which must match the oracle."""
+    A = planted_counts(1000, ncols, density=0.02, seed=ncols, dtype=dtype)
+    n_keep = 400
+    mask = salg.synth.make_mask(ncols, n_keep, seed=7)
+    x = salg.CsrMatrix.from_scipy(A, ctx)
+    om = salg.synth.make_omega(n_keep, 20, seed=42, dtype=dtype)
+    ref = O.sparse_pca_fit(A.astype(np.float64), 10, omega=om.astype(np.float64), mask=mask, n_oversamples=10,
+                           n_power_iterations=7)
+    pca = salg.MaskedSparsePCABuilder().n_components(10).mask(mask.tolist()).svd_method(_random(salg=salg)).build()
+    pca.fit(x, omega=om)
+    assert pca.components_.shape == (10, n_keep) and pca.mean_.shape == (ncols,)
+    assert np.allclose(pca.mean_, ref.mean, rtol=(1e-6 if dtype == np.float64 else 1e-4), atol=0)
+    assert abs(pca.total_var_ - ref.total_var) < (1e-6 if dtype == np.float64 else 1e-4) * ref.total_var
+    if dtype == np.float64:
+        assert O.rel_err(pca.singular_values_, ref.singular_values) < S_TOL_F64
+        assert O.largest_principal_angle(pca.components_, ref.components) < ANGLE_TOL
+    else:
+        # singular values only: the trailing components of this thin matrix sit in the noise floor, where an f32 subspace
+        # is gap-limited whatever the compaction does
+        assert O.rel_err(pca.singular_values_, ref.singular_values) < 1e-3
