@@ -41,7 +41,7 @@ enum salg_status {
     SALG_ERR_NOT_FITTED = 3,   /* "Must be fitted before transform!" (pca/sparse/mod.rs:259,263) */
     SALG_ERR_CUDA = 4,
     SALG_ERR_NCCL = 5,
-    SALG_ERR_NUMERIC = 6,      /* "SVD computation failed: ..." (pca/sparse/mod.rs:144,180) */
+    SALG_ERR_NUMERIC = 6,      /* "SVD computation failed: ..." (pca/sparse/mod.rs:144) / "Randomized SVD computation failed: ..." (:180) */
     SALG_ERR_UNSUPPORTED = 7,
     SALG_ERR_OOM = 8
 };

@@ -375,14 +375,14 @@ public:
     }
     // `feature_importances` (pca/sparse/mod.rs:295-302): squared loadings
     Array2<T> feature_importances() const {
-        if (!components_) throw Error(SALG_ERR_NOT_FITTED, "Must be fitted before transform!");
+        if (!components_) throw Error(SALG_ERR_NOT_FITTED, "Model must be fitted first!");          // :299
         Array2<T> out = *components_;
         for (auto& v : out.data) v = v * v;
         return out;
     }
     // `explained_variance_ratio` (pca/sparse/mod.rs:312-322): normalised by the sum over the COMPUTED components
     std::vector<T> explained_variance_ratio() const {
-        if (!explained_variance_) throw Error(SALG_ERR_NOT_FITTED, "Must be fitted before transform!");
+        if (!explained_variance_) throw Error(SALG_ERR_NOT_FITTED, "Model must be fitted first!");  // :316
         T total = T(0);
         for (T v : *explained_variance_) total += v;
         std::vector<T> r = *explained_variance_;

@@ -589,15 +589,15 @@ class _PCABase:
         return out
 
     def feature_importances(self):
-        """pca/sparse/mod.rs:295-302 — squared loadings (host; negligible)."""
+        """pca/sparse/mod.rs:295-302 — squared loadings (host; negligible); unfitted: "Model must be fitted first!" (:299)."""
         if self.components_ is None:
-            raise SalgError(N.ERR_NOT_FITTED, "Must be fitted before transform!")
+            raise SalgError(N.ERR_NOT_FITTED, "Model must be fitted first!")
         return self.components_ * self.components_
 
     def explained_variance_ratio(self):
         """pca/sparse/mod.rs:312-322 — normalised by the sum over the COMPUTED components."""
         if self.explained_variance_ is None:
-            raise SalgError(N.ERR_NOT_FITTED, "Must be fitted before transform!")
+            raise SalgError(N.ERR_NOT_FITTED, "Model must be fitted first!")
         ev = self.explained_variance_
         return ev / ev.sum()
 
@@ -610,14 +610,14 @@ class _PCABase:
         """explained_variance_ / total variance of the (kept, centred) columns — the scikit-learn definition; the
         reference divides by the sum over the computed components only (pca/sparse/mod.rs:318-319)."""
         if self.explained_variance_ is None:
-            raise SalgError(N.ERR_NOT_FITTED, "Must be fitted before transform!")
+            raise SalgError(N.ERR_NOT_FITTED, "Model must be fitted first!")
         return self.explained_variance_ / self.total_var_
 
     def noise_variance(self):
         """(total_var - sum explained) / (min(n_samples, n_features) - n_components): the value the reference prints under
         `verbose` (pca/sparse/mod.rs:225-238), returned; None when every component was computed."""
         if self.explained_variance_ is None:
-            raise SalgError(N.ERR_NOT_FITTED, "Must be fitted before transform!")
+            raise SalgError(N.ERR_NOT_FITTED, "Model must be fitted first!")
         min_dim = min(self._n_samples, self.components_.shape[1])
         d = len(self.explained_variance_)
         if d >= min_dim:

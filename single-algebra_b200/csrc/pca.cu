@@ -385,7 +385,10 @@ static salg_pca* pca_fit(salg_ctx* ctx, const salg_csr* x, const salg_pca_params
         P->explained_variance.resize(d_out);
         for (int i = 0; i < d_out; i++) {
             double s = P->singular_values[i];
-            SALG_REQUIRE(std::isfinite(s), SALG_ERR_NUMERIC, "SVD computation failed: non-finite singular value");
+            // the reference's two messages: pca/sparse/mod.rs:144 (Lanczos) and :180 (randomized)
+            SALG_REQUIRE(std::isfinite(s), SALG_ERR_NUMERIC,
+                         prm->svd_method == SALG_SVD_RANDOM ? "Randomized SVD computation failed: non-finite singular value"
+                                                            : "SVD computation failed: non-finite singular value");
             P->explained_variance[i] = s * s / (n_d - 1.0);   // pca/sparse/mod.rs:210-216
         }
         if (!center) {   // pca/sparse/mod.rs:218-223: without centring the total is the sum over components

@@ -248,6 +248,13 @@ static void test_masked() {
         threw = std::string(e.what()) == "Must be fitted before transform!";
     }
     CHECK(threw, "transform before fit");
+    threw = false;
+    try {
+        pca.explained_variance_ratio();
+    } catch (const Error& e) {
+        threw = std::string(e.what()) == "Model must be fitted first!";     // pca/sparse_masked/mod.rs:578
+    }
+    CHECK(threw, "explained_variance_ratio before fit");
     auto scores = pca.fit_transform(x);
     CHECK(scores.rows == rows && scores.cols == 10, "scores shape");
     CHECK(pca.components_->rows == 10 && pca.components_->cols == 200, "components_ cover the kept columns only");

@@ -33,7 +33,7 @@ def test_not_fitted_errors():
     for fn in (p.feature_importances, p.explained_variance_ratio, p.cumulative_explained_variance_ratio):
         with pytest.raises(s.SalgError) as e:
             fn()
-        assert str(e.value) == "Must be fitted before transform!"
+        assert str(e.value) == "Model must be fitted first!"      # pca/sparse/mod.rs:299, 316
 
 
 def test_partition_rows_by_nnz_balances_entries():
