@@ -368,6 +368,8 @@ public:
     // Default: the projection (X - 1 mu^T) V^T; TransformMode::ReferenceCompat reproduces the reference's loops bug for
     // bug.
     Array2<T> transform(const CsrMatrix<T>& x, TransformMode mode = TransformMode::Exact) const {
+        if (masked_ && x.ncols() != mask_len_)      // checked before the fitted state (pca/sparse_masked/mod.rs:440-444)
+            throw Error(SALG_ERR_MASK_LEN, "The mask vector length and the number of features (columns) have to be the same!");
         if (!model_) throw Error(SALG_ERR_NOT_FITTED, "Must be fitted before transform!");
         Array2<T> out{x.nrows(), components_->rows, std::vector<T>(x.nrows() * components_->rows)};
         check(Abi<T>::pca_transform(x.ctx().handle(), model_, x.device(), (int)mode, out.data.data()));
@@ -463,6 +465,7 @@ protected:
         n_components = o.n_components; alpha = o.alpha; tolerance = o.tolerance; random_seed = o.random_seed;
         center = o.center; verbose = o.verbose; svdmethod = o.svdmethod;
         model_ = o.model_; ctx_ = o.ctx_;
+        masked_ = o.masked_; mask_len_ = o.mask_len_;
         o.model_ = nullptr;
     }
 
@@ -474,6 +477,8 @@ protected:
     SVDMethod svdmethod;
     salg_pca* model_ = nullptr;
     salg_ctx* ctx_ = nullptr;
+    bool masked_ = false;            // MaskedSparsePCA: transform checks the mask length first
+    std::size_t mask_len_ = 0;
 };
 }  // namespace detail
 
@@ -541,6 +546,8 @@ public:
     MaskedSparsePCA(std::size_t n_components, T alpha, std::optional<T> tolerance, std::optional<std::uint32_t> random_seed,
                     bool center, bool verbose, std::vector<bool> mask, SVDMethod svdmethod)
         : mask_(std::move(mask)) {
+        this->masked_ = true;
+        this->mask_len_ = mask_.size();
         this->n_components = n_components;
         this->alpha = alpha;
         this->tolerance = tolerance.value_or(T(1e-6));

@@ -566,6 +566,9 @@ class _PCABase:
 
     def transform(self, x):
         """`transform(&self, x)` (pca/sparse/mod.rs:255, pca/sparse_masked/mod.rs:438)."""
+        if self._masked and x.ncols != len(self.mask):      # checked before the fitted state (pca/sparse_masked/mod.rs:440-444)
+            raise SalgError(N.ERR_MASK_LEN,
+                            "The mask vector length and the number of features (columns) have to be the same!")
         if self._model is None:
             raise SalgError(N.ERR_NOT_FITTED, "Must be fitted before transform!")
         lib = N.load()

@@ -36,6 +36,16 @@ def test_not_fitted_errors():
         assert str(e.value) == "Model must be fitted first!"      # pca/sparse/mod.rs:299, 316
 
 
+def test_masked_transform_checks_the_mask_length_before_the_fitted_state():
+    """pca/sparse_masked/mod.rs:440-444 comes before :449."""
+    import pytest
+    mp = s.MaskedSparsePCABuilder().mask([True, False, True]).build()
+    x = s.CsrMatrix(2, 4, np.array([0, 1, 2], np.uint64), np.array([0, 3], np.uint64), np.array([1.0, 2.0]))
+    with pytest.raises(s.SalgError) as e:
+        mp.transform(x)
+    assert e.value.code == 2 and "mask vector length" in str(e.value)
+
+
 def test_partition_rows_by_nnz_balances_entries():
     A = planted_counts(1000, 50, seed=1)
     A = sp.vstack([A, sp.csr_matrix((200, 50))]).tocsr()      # trailing empty rows
