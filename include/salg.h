@@ -135,6 +135,16 @@ int salg_csr_download_raw(salg_ctx* ctx, const salg_csr* csr, int64_t* row_offse
  * renumbered by rank among kept columns; bit-exact with `A[:, mask]`. */
 int salg_csr_select_columns(salg_ctx* ctx, const salg_csr* csr, const uint8_t* mask,
                             int64_t mask_len, salg_csr** out);
+/* Device CSR <-> CSC: a NEW handle holding the CSR of A^T — i.e. the CSC arrays of A (col_offsets,
+ * row_indices ascending within a column, values) — built by a stable sort of the entries by column.  ncols(out) = nrows(in).
+ * Applied to a handle from salg_csc_upload_* it returns the CSR of A.  The input keeps the transposed copy cached for its
+ * own gather-form A^T products.  Per-GPU limit: < 2^31 stored entries (32-bit sort positions). */
+int salg_csr_transpose(salg_ctx* ctx, const salg_csr* csr, salg_csr** out);
+/* Device copy of the value array (same type, nnz + 16 entries) and its restore: lets a caller run the in-place
+ * Normalize / Log1P chain repeatedly from the same raw counts without another upload.  Free the clone with salg_dev_free. */
+int salg_csr_values_clone(salg_ctx* ctx, const salg_csr* csr, void** clone);
+int salg_csr_values_restore(salg_ctx* ctx, salg_csr* csr, const void* clone);
+int salg_dev_free(salg_ctx* ctx, void* p);
 /* Device-side synthetic count-matrix generator (bench input; not a reference function). Rows
  * [row0, row0+nrows) of the matrix defined by the tables (see single-algebra_b200/synth.py). */
 int salg_csr_synth(salg_ctx* ctx, int dtype, uint64_t seed, int64_t row0, int64_t nrows,
@@ -151,11 +161,16 @@ int salg_sum_col_f64(salg_ctx* ctx, const salg_csr* csr, double* sum, double* su
 /* sum_row (src/sparse/csr.rs:314-392) */
 int salg_sum_row_f32(salg_ctx* ctx, const salg_csr* csr, float* out);
 int salg_sum_row_f64(salg_ctx* ctx, const salg_csr* csr, double* out);
-/* MatrixNonZero::nonzero_col / nonzero_row (src/sparse/csr.rs:23-122) and MatrixVariance::var_col
- * (:632-678) — SURVEY §8f-1; they fall out of the same pass. `var` uses the reference's
- * (sumsq/n - mean^2) * n/(n-1). Any pointer may be NULL. */
+/* MatrixNonZero::nonzero_col (src/sparse/csr.rs:23-77) and MatrixVariance::var_col (:632-678) — SURVEY §8f-1; they fall
+ * out of the same pass. `var` uses the reference's (sumsq/n - mean^2) * n/(n-1). Any pointer may be NULL. */
 int salg_col_stats_f64(salg_ctx* ctx, const salg_csr* csr, double* sum, double* sumsq,
                        double* nnz_col, double* var_col);
+
+/* MatrixNonZero::nonzero_row (src/sparse/csr.rs:79-122): stored entries per row = row_offsets[r+1] - row_offsets[r],
+ * out[nrows]; MatrixNonZero::nonzero_col (:23-77): stored entries per column, out[ncols] (all-reduced under a dist ctx).
+ * The reference is generic over unsigned integer T; the ABI returns u64 and the facade narrows. */
+int salg_nonzero_row(salg_ctx* ctx, const salg_csr* csr, uint64_t* out);
+int salg_nonzero_col(salg_ctx* ctx, const salg_csr* csr, uint64_t* out);
 
 /* ---- Normalize / Log1P (src/utils/mod.rs:6-17) ----------------------------------------------- */
 /* Normalize::normalize for CsrMatrix (src/sparse/csr.rs:1013-1068), in place on the device values:
@@ -271,8 +286,6 @@ int salg_op_cholqr2_f64(salg_ctx* ctx, const double* panel, int64_t m, int64_t k
 /* Singular values (descending) and right/left factors of a host k x k matrix by the one-CTA
  * Jacobi kernel: a = u * diag(s) * vt. */
 int salg_op_small_svd(salg_ctx* ctx, const double* a, int64_t k, double* u, double* s, double* vt);
-/* Repeats one centred SpMM (transposed or not) `iters` times on a device-resident random panel and
- * returns the average device ms — the microbenchmark behind bench.py's roofline object. */
 /* Test / probe hook for the fused tall-panel pass of the f32 tensor-core path (tc.cu: tc_gram_prep_kernel): Gram matrix
  * (k x k row-major) and column sums of a panel in one pass, f32 products exact in fp16 two-term form, f32 accumulation
  * drained to f64 every 1024 rows.  It replaces the Gram of nalgebra's qr()/lu() replacement (CholeskyQR) on the tall
@@ -281,6 +294,8 @@ int salg_op_small_svd(salg_ctx* ctx, const double* a, int64_t k, double* u, doub
 int salg_op_tall_gram_f32(salg_ctx* ctx, const float* panel, int64_t m, int64_t k, int64_t device_rows, double* gram,
                           double* colsum, int iters, double* avg_ms);
 
+/* Repeats one centred SpMM (transposed or not) `iters` times on a device-resident random panel and
+ * returns the average device ms — a microbenchmark of the product kernels (tools/scripts_tc_*.py). */
 int salg_op_spmm_bench(salg_ctx* ctx, const salg_csr* csr, int transposed, int64_t k, int iters,
                        double* avg_ms);
 

@@ -506,7 +506,11 @@ public:
     // `fit_transform(&mut self, x)` (pca/sparse/mod.rs:355-358): fit, then the projection of the same rows (computed inside
     // the fit call while the operator is resident)
     Array2<T> fit_transform(const CsrMatrix<T>& x, const T* omega = nullptr, std::size_t omega_rows = 0,
-                            std::size_t omega_cols = 0) {
+                            std::size_t omega_cols = 0, TransformMode mode = TransformMode::Exact) {
+        if (mode != TransformMode::Exact) {          // fit + transform literally: the projection kept by the fit is the exact one
+            this->fit_impl(x, nullptr, false, omega, omega_rows, omega_cols);
+            return this->transform(x, mode);
+        }
         this->fit_impl(x, nullptr, true, omega, omega_rows, omega_cols);
         return this->fit_scores(x.nrows());
     }
@@ -565,7 +569,11 @@ public:
     }
     // `fit_transform(&mut self, x)` (pca/sparse_masked/mod.rs:605-619)
     Array2<T> fit_transform(const CsrMatrix<T>& x, const T* omega = nullptr, std::size_t omega_rows = 0,
-                            std::size_t omega_cols = 0) {
+                            std::size_t omega_cols = 0, TransformMode mode = TransformMode::Exact) {
+        if (mode != TransformMode::Exact) {
+            this->fit_impl(x, &mask_, false, omega, omega_rows, omega_cols);
+            return this->transform(x, mode);
+        }
         this->fit_impl(x, &mask_, true, omega, omega_rows, omega_cols);
         return this->fit_scores(x.nrows());
     }

@@ -70,6 +70,12 @@ PROTOTYPES = {
     "salg_csr_download_f64": [_P, _P, _P, _P, _P],
     "salg_csr_download_raw": [_P, _P, _P, _P, _P],
     "salg_csr_select_columns": [_P, _P, _P, _i64, C.POINTER(_P)],
+    "salg_csr_transpose": [_P, _P, C.POINTER(_P)],
+    "salg_csr_values_clone": [_P, _P, C.POINTER(_P)],
+    "salg_csr_values_restore": [_P, _P, _P],
+    "salg_dev_free": [_P, _P],
+    "salg_nonzero_row": [_P, _P, _P],
+    "salg_nonzero_col": [_P, _P, _P],
     "salg_csr_synth": [_P, _int, C.c_uint64, _i64, _i64, _i64, C.c_int32, _P, _P, _P, C.POINTER(_P)],
     "salg_sum_col_f32": [_P, _P, _P, _P],
     "salg_sum_col_f64": [_P, _P, _P, _P],

@@ -205,6 +205,36 @@ class DeviceCsr:
         N.check(N.load().salg_csr_select_columns(self.ctx._h, self._h, N.ptr(m), len(m), C.byref(h)))
         return DeviceCsr(h, self.ctx)
 
+    def transpose(self) -> "DeviceCsr":
+        """New handle holding the CSR of A^T (= the CSC arrays of A); device-side stable sort by column."""
+        h = C.c_void_p()
+        N.check(N.load().salg_csr_transpose(self.ctx._h, self._h, C.byref(h)))
+        return DeviceCsr(h, self.ctx)
+
+    def clone_values(self):
+        """Opaque device copy of the value array (restore_values puts it back: the in-place Normalize / Log1P chain can
+        then be repeated from the same raw counts without another upload)."""
+        h = C.c_void_p()
+        N.check(N.load().salg_csr_values_clone(self.ctx._h, self._h, C.byref(h)))
+        return h
+
+    def restore_values(self, clone):
+        N.check(N.load().salg_csr_values_restore(self.ctx._h, self._h, clone))
+
+    def free_values_clone(self, clone):
+        N.check(N.load().salg_dev_free(self.ctx._h, clone))
+
+    # MatrixNonZero (src/sparse/csr.rs:23-122) -------------------------------------------------------
+    def nonzero_row(self):
+        out = np.empty(self.nrows, np.uint64)
+        N.check(N.load().salg_nonzero_row(self.ctx._h, self._h, N.ptr(out)))
+        return out
+
+    def nonzero_col(self):
+        out = np.empty(self.ncols, np.uint64)
+        N.check(N.load().salg_nonzero_col(self.ctx._h, self._h, N.ptr(out)))
+        return out
+
     # MatrixSum ------------------------------------------------------------------------------------
     def sum_col(self):
         out = np.empty(self.ncols, self.dtype)
@@ -254,6 +284,11 @@ class DeviceCsr:
         fn = getattr(N.load(), f"salg_preprocess_{self._sfx}")
         N.check(fn(self.ctx._h, self._h, float(target), N.ptr(s), N.ptr(q)))
         return s, q
+
+    def preprocess_device(self, target):
+        """The same fused chain with nothing copied back (the statistics are recomputed by the fit that follows)."""
+        fn = getattr(N.load(), f"salg_preprocess_{self._sfx}")
+        N.check(fn(self.ctx._h, self._h, float(target), None, None))
 
     def free(self):
         if self._h:
@@ -337,6 +372,13 @@ class CsrMatrix:
 
     def sum_row(self):
         return self.to_device().sum_row()
+
+    # MatrixNonZero (src/sparse/csr.rs:23-122) ----------------------------------------------------------
+    def nonzero_col(self):
+        return self.to_device().nonzero_col()
+
+    def nonzero_row(self):
+        return self.to_device().nonzero_row()
 
     # Normalize / Log1P (src/sparse/csr.rs:1013-1079) ------------------------------------------------------
     def normalize(self, sums, target, direction):
@@ -528,6 +570,12 @@ class _PCABase:
         self._model = h
         self._dtype = d.dtype
         self._ctx = d.ctx
+        flags = self.numeric_flags()
+        if flags & 4:
+            import warnings
+            warnings.warn("Lanczos stopped at its step limit before every requested singular triplet met the acceptance "
+                          "bound; the returned components are the best available (numeric_flags() & 4)", RuntimeWarning,
+                          stacklevel=3)
         if fetch:
             self._fetch()
         return self
@@ -581,6 +629,14 @@ class _PCABase:
     def fit_transform(self, x, omega=None, out=None):
         """`fit_transform(&mut self, x)` (pca/sparse/mod.rs:355-358): fit, then the projection of the
         same rows; the projection runs inside the fit call while the compacted operator is resident."""
+        if self.transform_mode != N.TRANSFORM_EXACT:
+            # fit + transform literally (pca/sparse/mod.rs:355-358): the projection kept by the fit is the EXACT one
+            self._fit(x, omega, keep_scores=False)
+            sc = self.transform(x)
+            if out is not None:
+                out[...] = sc
+                return out
+            return sc
         self._fit(x, omega, keep_scores=True)
         lib = N.load()
         sfx = "f64" if self._dtype == np.float64 else "f32"

@@ -426,6 +426,16 @@ void csr_ensure_transpose(salg_ctx* ctx, const salg_csr* c) {
 template void csr_ensure_transpose<float>(salg_ctx*, const salg_csr*);
 template void csr_ensure_transpose<double>(salg_ctx*, const salg_csr*);
 
+// stored entries per row: row_offsets[r + 1] - row_offsets[r]  (MatrixNonZero::nonzero_row, src/sparse/csr.rs:79-122)
+__global__ void row_nnz_kernel(const int64_t* __restrict__ ptr, int64_t nrows, uint64_t* __restrict__ out) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < nrows) out[r] = (uint64_t)(ptr[r + 1] - ptr[r]);
+}
+__global__ void f64_to_u64_kernel(const double* __restrict__ in, int64_t n, uint64_t* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint64_t)llrint(in[i]);
+}
+
 }  // namespace salg
 
 using namespace salg;
@@ -508,6 +518,91 @@ int salg_csr_download_raw(salg_ctx* ctx, const salg_csr* c, int64_t* off, uint32
         if (idx && c->nnz) SALG_CUDA(cudaMemcpyAsync(idx, c->col, (size_t)c->nnz * 4, cudaMemcpyDeviceToHost, st));
         if (val && c->nnz) SALG_CUDA(cudaMemcpyAsync(val, c->val, (size_t)c->nnz * es, cudaMemcpyDeviceToHost, st));
         SALG_CUDA(cudaStreamSynchronize(st));
+    });
+}
+
+int salg_csr_transpose(salg_ctx* ctx, const salg_csr* c, salg_csr** out) {
+    return guarded([&] {
+        SALG_REQUIRE(ctx && c && out, SALG_ERR_BAD_ARG, "ctx/csr/out is NULL");
+        SALG_REQUIRE(ctx->nranks == 1, SALG_ERR_UNSUPPORTED, "transpose of a row-sharded matrix is not a local operation");
+        SALG_CUDA(cudaSetDevice(ctx->device));
+        cudaStream_t st = ctx->stream;
+        if (c->dtype == SALG_F64) csr_ensure_transpose<double>(ctx, c);
+        else csr_ensure_transpose<float>(ctx, c);
+        salg_csr* t = csr_alloc(ctx, c->dtype, c->ncols, c->nrows, c->nnz);
+        const size_t es = dsize(c->dtype);
+        SALG_CUDA(cudaMemcpyAsync(t->row_ptr, c->t_ptr, (size_t)(c->ncols + 1) * 8, cudaMemcpyDeviceToDevice, st));
+        SALG_CUDA(cudaMemcpyAsync(t->col, c->t_idx, ((size_t)c->nnz + 16) * 4, cudaMemcpyDeviceToDevice, st));
+        SALG_CUDA(cudaMemcpyAsync(t->val, c->t_val, ((size_t)c->nnz + 16) * es, cudaMemcpyDeviceToDevice, st));
+        SALG_CUDA(cudaStreamSynchronize(st));
+        *out = t;
+    });
+}
+
+int salg_nonzero_row(salg_ctx* ctx, const salg_csr* c, uint64_t* out) {
+    return guarded([&] {
+        SALG_REQUIRE(ctx && c, SALG_ERR_BAD_ARG, "ctx/csr is NULL");
+        if (c->nrows == 0) return;                                   // src/sparse/csr.rs:87-89
+        SALG_REQUIRE(out, SALG_ERR_BAD_ARG, "out is NULL");
+        SALG_CUDA(cudaSetDevice(ctx->device));
+        cudaStream_t st = ctx->stream;
+        DevBuf<uint64_t> d((size_t)c->nrows, st);
+        row_nnz_kernel<<<(unsigned)ceil_div(c->nrows, 256), 256, 0, st>>>(c->row_ptr, c->nrows, d.get());
+        ctx->n_launch++;
+        SALG_CUDA(cudaGetLastError());
+        SALG_CUDA(cudaMemcpyAsync(out, d.get(), (size_t)c->nrows * 8, cudaMemcpyDeviceToHost, st));
+        SALG_CUDA(cudaStreamSynchronize(st));
+    });
+}
+
+int salg_nonzero_col(salg_ctx* ctx, const salg_csr* c, uint64_t* out) {
+    return guarded([&] {
+        SALG_REQUIRE(ctx && c, SALG_ERR_BAD_ARG, "ctx/csr is NULL");
+        if (c->ncols == 0) return;
+        SALG_REQUIRE(out, SALG_ERR_BAD_ARG, "out is NULL");
+        SALG_CUDA(cudaSetDevice(ctx->device));
+        cudaStream_t st = ctx->stream;
+        const size_t n = (size_t)c->ncols;
+        DevBuf<double> d_sum(n, st), d_cnt(n, st);
+        if (c->dtype == SALG_F64) col_stats_device<double>(ctx, c, d_sum.get(), nullptr, d_cnt.get());
+        else col_stats_device<float>(ctx, c, d_sum.get(), nullptr, d_cnt.get());
+        DevBuf<uint64_t> d(n, st);
+        f64_to_u64_kernel<<<(unsigned)ceil_div((int64_t)n, 256), 256, 0, st>>>(d_cnt.get(), (int64_t)n, d.get());
+        ctx->n_launch++;
+        SALG_CUDA(cudaGetLastError());
+        SALG_CUDA(cudaMemcpyAsync(out, d.get(), n * 8, cudaMemcpyDeviceToHost, st));
+        SALG_CUDA(cudaStreamSynchronize(st));
+    });
+}
+
+int salg_csr_values_clone(salg_ctx* ctx, const salg_csr* c, void** out) {
+    return guarded([&] {
+        SALG_REQUIRE(ctx && c && out, SALG_ERR_BAD_ARG, "ctx/csr/out is NULL");
+        SALG_CUDA(cudaSetDevice(ctx->device));
+        const size_t bytes = ((size_t)c->nnz + 16) * dsize(c->dtype);
+        void* p = dev_alloc(ctx, bytes);
+        SALG_CUDA(cudaMemcpyAsync(p, c->val, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        *out = p;
+    });
+}
+
+int salg_csr_values_restore(salg_ctx* ctx, salg_csr* c, const void* clone) {
+    return guarded([&] {
+        SALG_REQUIRE(ctx && c && clone, SALG_ERR_BAD_ARG, "ctx/csr/clone is NULL");
+        SALG_CUDA(cudaSetDevice(ctx->device));
+        if (c->t_valid || c->tc) {                       // values change: cached transposed copy / tile format are stale
+            SALG_CUDA(cudaStreamSynchronize(ctx->stream));
+            csr_invalidate_transpose(c);
+        }
+        SALG_CUDA(cudaMemcpyAsync(c->val, clone, ((size_t)c->nnz + 16) * dsize(c->dtype), cudaMemcpyDeviceToDevice,
+                                  ctx->stream));
+    });
+}
+
+int salg_dev_free(salg_ctx* ctx, void* p) {
+    return guarded([&] {
+        SALG_REQUIRE(ctx, SALG_ERR_BAD_ARG, "ctx is NULL");
+        dev_free(ctx, p);
     });
 }
 

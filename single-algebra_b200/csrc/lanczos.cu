@@ -276,16 +276,30 @@ int lanczos_svd(salg_ctx* ctx, const salg_csr* op, int k, int max_steps, uint64_
     cudaStream_t st = ctx->stream;
     const int64_t nr = op->nrows, n = op->ncols;
     const int64_t nr_total = global_nrows(ctx, nr);
+    // step limit: the reference passes iterations = max(n_samples, n_features) (pca/sparse/mod.rs:134-142), which las2
+    // clamps to min(nrows, ncols); lanczos_max_steps > 0 lowers it
     int64_t mmax = std::min<int64_t>(n, nr_total);
     if (max_steps > 0) mmax = std::min<int64_t>(mmax, max_steps);
-    else mmax = std::min<int64_t>(mmax, 1500);
     SALG_REQUIRE(mmax >= 1, SALG_ERR_BAD_ARG, "empty operator");
     const int m = (int)mmax;
     csr_ensure_transpose<T>(ctx, op);
     const double eps_t = sizeof(T) == 4 ? 1.2e-7 : 2.3e-16;
 
-    DevBuf<T> Vb((size_t)(m + 1) * n, st), Ub((size_t)m * (nr > 0 ? nr : 1), st), wu((size_t)(nr > 0 ? nr : 1), st),
-        wv((size_t)n, st);
+    // The two Krylov bases grow with the iteration (capacity doubles from max(128, 2k) steps): allocating them for the
+    // step LIMIT would need (n + nrows) * min(n, nrows) values — 120 GB for the reference's own 10M x 2500 test shape —
+    // when convergence takes ~100-300 steps.
+    const size_t nr1 = (size_t)(nr > 0 ? nr : 1);
+    int cap = (int)std::min<int64_t>(m, std::max(128, 2 * k + 20));
+    DevBuf<T> Vb((size_t)(cap + 1) * n, st), Ub((size_t)cap * nr1, st), wu(nr1, st), wv((size_t)n, st);
+    auto grow = [&](int used) {            // `used` steps (and used + 1 right vectors) are live
+        const int ncap = (int)std::min<int64_t>(m, (int64_t)cap * 2);
+        DevBuf<T> nV((size_t)(ncap + 1) * n, st), nU((size_t)ncap * nr1, st);
+        SALG_CUDA(cudaMemcpyAsync(nV.get(), Vb.get(), (size_t)(used + 1) * n * sizeof(T), cudaMemcpyDeviceToDevice, st));
+        SALG_CUDA(cudaMemcpyAsync(nU.get(), Ub.get(), (size_t)used * nr1 * sizeof(T), cudaMemcpyDeviceToDevice, st));
+        Vb = std::move(nV);
+        Ub = std::move(nU);
+        cap = ncap;
+    };
     DevBuf<double> coef((size_t)m + 1, st), alpha((size_t)m, st), beta((size_t)m, st), sq(1, st);
     SALG_CUDA(cudaMemsetAsync(alpha.get(), 0, (size_t)m * 8, st));
     SALG_CUDA(cudaMemsetAsync(beta.get(), 0, (size_t)m * 8, st));
@@ -339,6 +353,7 @@ int lanczos_svd(salg_ctx* ctx, const salg_csr* op, int k, int max_steps, uint64_
     bool converged = false;
     const int check_every = 20;
     for (int j = 0; j < m; j++) {
+        if (j == cap) grow(j);
         // u_j
         spmv<T>(ctx, op->row_ptr, op->col, (const T*)op->val, nr, n, op->nnz, Vb.get() + (size_t)j * n, wu.get());
         reorth(Ub.get(), nr, j, wu.get(), ctx->nranks > 1);

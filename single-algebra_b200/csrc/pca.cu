@@ -231,7 +231,10 @@ static salg_pca* pca_fit(salg_ctx* ctx, const salg_csr* x, const salg_pca_params
         int d_out = rank;
 
         if (prm->svd_method == SALG_SVD_RANDOM) {
-            const int l = rank + std::max(0, prm->n_oversamples);
+            // l = rank + n_oversamples, clamped to the dimensions of the operator: a wider sketch is rank-deficient by
+            // construction (CholeskyQR would then run on its pivot floor), and min(n, n_eff) columns already span everything
+            const int l_req = rank + std::max(0, prm->n_oversamples);
+            const int l = (int)std::min<int64_t>(l_req, std::min<int64_t>(n_total, n_eff));
             SALG_REQUIRE(l <= LP, SALG_ERR_UNSUPPORTED,
                          "n_components + n_oversamples must be <= 64 (device panels are 64 columns wide)");
             const int q = std::max(0, prm->n_power_iterations);
@@ -241,10 +244,18 @@ static salg_pca* pca_fit(salg_ctx* ctx, const salg_csr* x, const salg_pca_params
             DevBuf<double> corr(LP, st), cs(LP, st), Rb(LP * LP, st), Ur(LP * LP, st), Sr(LP, st), Vr(LP * LP, st);
             DevBuf<T> M64(LP * LP, st);
             if (omega) {
-                SALG_REQUIRE(omega_rows == n_eff && omega_cols == l, SALG_ERR_BAD_ARG,
+                SALG_REQUIRE(omega_rows == n_eff && (omega_cols == l || omega_cols == l_req), SALG_ERR_BAD_ARG,
                              "omega must be (kept columns) x (rank + n_oversamples), row-major");
                 DevBuf<T> raw((size_t)n_eff * l, st);
-                SALG_CUDA(cudaMemcpyAsync(raw.get(), omega, (size_t)n_eff * l * sizeof(T), cudaMemcpyHostToDevice, st));
+                std::vector<T> lead;                                // clamped sketch: the leading l columns of omega
+                const T* src = omega;
+                if (omega_cols != l) {
+                    lead.resize((size_t)n_eff * l);
+                    for (int64_t i = 0; i < n_eff; i++)
+                        std::copy(omega + i * omega_cols, omega + i * omega_cols + l, lead.begin() + i * l);
+                    src = lead.data();
+                }
+                SALG_CUDA(cudaMemcpyAsync(raw.get(), src, (size_t)n_eff * l * sizeof(T), cudaMemcpyHostToDevice, st));
                 panel_pack<T>(ctx, raw.get(), n_eff, l, Om.get());
                 SALG_CUDA(cudaStreamSynchronize(st));
             } else {

@@ -33,17 +33,20 @@ namespace salg {
 
 constexpr int TC_RB = 128;          // tile rows
 constexpr int TC_CB = 64;           // tile columns
-// The scatter role is latency-bound (barrier hand-offs, shared-memory round trips, proxy fence), not issue-bound, so
-// it is split into independent GROUPS: group g owns sparse-operand buffer g and builds every TC_GROUPS-th unit while the
-// other groups build theirs and the tensor core consumes an earlier one.
+// The scatter role is split into independent GROUPS: group g builds every TC_GROUPS-th unit while the other groups build
+// theirs and the tensor core consumes earlier ones.  Buffers are NOT tied to groups: pass P (unit * terms + term) goes to
+// buffer P % NSB, so a group can start its next unit while its previous one still waits for the tensor core.
+// Measured on B200 (profiles/r02_tc_variants.md): 2 groups x 8 warps with 4 buffers (A X; two 16 KB panel stages instead
+// of four pay for the fourth buffer) / 3 buffers (A^T Y) beat 3 x 5 with 3 buffers by 8 % / 8 %; one group of 15 or 16
+// warps building unit after unit is 30 % slower (the units' hand-off chains no longer overlap).
 #ifndef TC_GROUP_WARPS_
-#define TC_GROUP_WARPS_ 5
+#define TC_GROUP_WARPS_ 8
 #endif
 #ifndef TC_UNSCATTER_
 #define TC_UNSCATTER_ 0
 #endif
 #ifndef TC_GROUPS_
-#define TC_GROUPS_ 3
+#define TC_GROUPS_ 2
 #endif
 #ifndef TC_SLOT_ENTRIES_
 #define TC_SLOT_ENTRIES_ 768
@@ -52,7 +55,7 @@ constexpr int TC_CB = 64;           // tile columns
 #define TC_NS_ 5
 #endif
 #ifndef TC_AX_NB_
-#define TC_AX_NB_ 4
+#define TC_AX_NB_ 2
 #endif
 #ifndef TC_ATY_NS_
 #define TC_ATY_NS_ TC_NS_
@@ -73,7 +76,14 @@ constexpr int TC_RPAD = 4;            // row blocks are padded to a multiple of 
 constexpr int TC_SLOT_ENTRIES = TC_SLOT_ENTRIES_;  // entries per ring slot (one tile); denser tiles read their tail from global memory
 constexpr int TC_SLOT_BYTES = (TC_SLOT_ENTRIES + 2) * 8;
 constexpr int TC_S_BYTES = 32768;     // sparse operand buffer: 256 x 64 (A X) or 128 x 128 (A^T Y) fp16
-constexpr int TC_NSB = TC_GROUPS;     // sparse operand buffers: one per scatter group
+#ifndef TC_NSB_
+#define TC_NSB_ 4
+#endif
+#ifndef TC_ATY_NSB_
+#define TC_ATY_NSB_ 3
+#endif
+constexpr int TC_NSB = TC_NSB_;       // sparse operand buffers (A X): pass P (unit * terms + term) uses buffer P % NSB
+constexpr int TC_ATY_NSB = TC_ATY_NSB_;   // the same for A^T Y (its dense stages are twice as large)
 constexpr int TC_EPT = (TC_SLOT_ENTRIES + TC_GROUP_THREADS - 1) / TC_GROUP_THREADS;   // ring entries per thread and tile
 constexpr uint32_t TC_SPIN_LIMIT = 1u << 24;
 // suspend-time hint of mbarrier.try_wait: a waiting thread sleeps in hardware until the phase completes (or this many
@@ -291,7 +301,7 @@ __global__ void __launch_bounds__(TC_BIN_THREADS, 2)
 tc_bin_kernel(const int64_t* __restrict__ in_ptr, int in_shift, const int64_t* __restrict__ ptr, const uint32_t* __restrict__ col,
               const T* __restrict__ val, int64_t nrows,
               int64_t nnz, int n_rb, int n_cb, uint2* __restrict__ entries, int64_t* __restrict__ tile_ptr,
-              unsigned* __restrict__ info /* [0] inexact flag, [1] bits of max |v| */) {
+              unsigned* __restrict__ info /* [0] inexact flag, [1] bits of max |v| */, int rot) {
     extern __shared__ unsigned bin_sm[];
     unsigned* hist = bin_sm;             // [n_cb] counts, then running cursors
     __shared__ unsigned s_warp[TC_BIN_THREADS / 32];
@@ -317,8 +327,12 @@ tc_bin_kernel(const int64_t* __restrict__ in_ptr, int in_shift, const int64_t* _
         constexpr int RPW = TC_RB / NW;                        // rows per warp
         int64_t my_s = 0;
         uint32_t my_len = 0;
+        // rows of this warp: interleaved (warp + NW i), or — `rot` — the 8 consecutive rows 8 warp .. 8 warp + 7 visited
+        // in an order rotated by the warp index, so that warps running side by side place entries of DIFFERENT
+        // (row & 7) classes into a tile (the shared-memory bank of an entry in the products is 4 (row & 7) + ...)
+        auto local_row = [&](int i) -> unsigned { return rot ? (unsigned)(RPW * warp + ((i + warp) & (RPW - 1))) : (unsigned)(warp + NW * i); };
         if (lane < RPW) {
-            const int64_t r = r0 + warp + (int64_t)NW * lane;
+            const int64_t r = r0 + local_row(lane);
             if (r < r1) {
                 const int64_t a0 = ptr[r];
                 my_s = in_ptr[r] >> in_shift;
@@ -382,7 +396,7 @@ tc_bin_kernel(const int64_t* __restrict__ in_ptr, int in_shift, const int64_t* _
             const uint32_t* __restrict__ cr = col + s;
             const T* __restrict__ vr = val + s;
             const uint32_t last = len - 1;
-            const unsigned lr = (unsigned)(warp + NW * i);
+            const unsigned lr = local_row(i);
             for (uint32_t p0 = 0; p0 < len; p0 += 32 * BU) {
                 uint32_t cc[BU];
                 T vv[BU];
@@ -525,7 +539,8 @@ void* tc_build(salg_ctx* ctx, const salg_csr* c, const int64_t* in_ptr = nullptr
             const size_t sm = (size_t)t->n_cb * sizeof(unsigned);
             int grid = t->n_rb < ctx->sm_count * 4 ? t->n_rb : ctx->sm_count * 4;
             tc_bin_kernel<T><<<grid, TC_BIN_THREADS, sm, st>>>(in_ptr, in_shift, c->row_ptr, in_col, in_val, c->nrows, nnz, t->n_rb,
-                                                              t->n_cb, t->entries, t->tile_ptr, info.get());
+                                                              t->n_cb, t->entries, t->tile_ptr, info.get(),
+                                                              getenv("SALG_TC_ROT") ? atoi(getenv("SALG_TC_ROT")) : 0);
             ctx->n_launch++;
             SALG_CUDA(cudaGetLastError());
         }
@@ -670,11 +685,24 @@ struct TcSeq {
 
 struct alignas(16) TcSlotMeta { long long e0[2]; int n[2]; int pad[2]; };   // per tile: first entry, entry count, leading pad (0/1)
 
+// L2 prefetch of the entry lists of one unit (tile pointers o[0..3] as in tc_entry_loader)
+__device__ __forceinline__ void tc_prefetch_unit(const uint2* __restrict__ entries, const long long (&o)[4], bool two) {
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        if (k == 1 && !two) break;
+        const long long e0 = o[2 * k] & ~1LL, e1 = o[2 * k + 1];
+        if (e1 > e0) {
+            const uint32_t bytes = (uint32_t)(((e1 - e0) * 8 + 15) & ~15LL);
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(entries + e0), "r"(bytes) : "memory");
+        }
+    }
+}
+
 // ---- entry loader role ---------------------------------------------------------------------------------------------------
 template <int NS>
 __device__ __forceinline__ void tc_entry_loader(const uint2* __restrict__ entries, const int64_t* __restrict__ tile_ptr,
                                                 const TcSeq& seq, uint8_t* sRing, TcSlotMeta* sMeta, uint64_t* e_full,
-                                                uint64_t* e_free, int w) {
+                                                uint64_t* e_free, int w, int pfd, int dbg = 0) {
     const int64_t nu = seq.n_units();
     long long p[4] = {0, 0, 0, 0};       // tile pointers of the current unit: [e0, e1) of tile 0, [e0, e1) of tile 1
     bool two = false;
@@ -687,11 +715,21 @@ __device__ __forceinline__ void tc_entry_loader(const uint2* __restrict__ entrie
         o[2] = o_two ? tile_ptr[t1] : 0;
         o[3] = o_two ? tile_ptr[t1 + 1] : 0;
     };
+    // L2 prefetch of the entry lists `pfd` units ahead: the ring holds NS units (~9 KB each), far less than the bytes a
+    // B200 SM must keep in flight to cover DRAM latency at its share of the HBM bandwidth; with the lists already in L2
+    // the ring's bulk copies complete in L2 latency instead
+    long long pf[4] = {0, 0, 0, 0};
+    bool pf_two = false;
+    if (pfd > 0 && w + pfd < nu) fetch(w + pfd, pf, pf_two);
     if (w < nu) fetch(w, p, two);
     for (int64_t s = w; s < nu; s += NS) {           // loader w owns ring slot w
         long long np[4] = {0, 0, 0, 0};
         bool ntwo = false;
         if (s + NS < nu) fetch(s + NS, np, ntwo);   // next unit's pointers, overlapped
+        if (pfd > 0) {
+            if (s + pfd < nu) tc_prefetch_unit(entries, pf, pf_two);
+            if (s + NS + pfd < nu) fetch(s + NS + pfd, pf, pf_two);
+        }
         const int slot = (int)(s % NS);
         const uint32_t use = (uint32_t)(s / NS);
         if (use > 0) mbar_wait(&e_free[slot], (use - 1) & 1);
@@ -709,7 +747,7 @@ __device__ __forceinline__ void tc_entry_loader(const uint2* __restrict__ entrie
             sMeta[slot].pad[k] = pad;
             bytes[k] = (uint32_t)cnt * 8u;
         }
-        if (bytes[0] + bytes[1] > 0) {
+        if (bytes[0] + bytes[1] > 0 && !(dbg & 64)) {                  // (dbg 64: timing experiment, no entry loads)
             mbar_expect_tx(&e_full[slot], bytes[0] + bytes[1]);
             uint8_t* dst = sRing + (size_t)slot * (2 * TC_SLOT_BYTES);
             if (bytes[0]) bulk_g2s(dst, entries + (p[0] - (p[0] & 1)), bytes[0], &e_full[slot]);
@@ -721,6 +759,24 @@ __device__ __forceinline__ void tc_entry_loader(const uint2* __restrict__ entrie
         for (int k = 0; k < 4; k++) p[k] = np[k];
         two = ntwo;
     }
+}
+
+// the first `pfd` units of a CTA are prefetched by all lanes of the loader warps at kernel start
+__device__ __forceinline__ void tc_prefetch_prologue(const uint2* __restrict__ entries, const int64_t* __restrict__ tile_ptr,
+                                                     const TcSeq& seq, int pfd, int t) {
+    const int64_t nu = seq.n_units();
+    for (int64_t u = t; u < pfd && u < nu; u += TC_LOADER_WARPS * 32) {
+        int64_t t0, t1;
+        seq.tiles(u, t0, t1);
+        long long o[4];
+        o[0] = tile_ptr[t0];
+        o[1] = tile_ptr[t0 + 1];
+        const bool two = t1 >= 0;
+        o[2] = two ? tile_ptr[t1] : 0;
+        o[3] = two ? tile_ptr[t1 + 1] : 0;
+        tc_prefetch_unit(entries, o, two);
+    }
+    __syncwarp();
 }
 
 // ---- scatter role -----------------------------------------------------------------------------------------------------------
@@ -737,14 +793,13 @@ __device__ __forceinline__ void tc_scatter_one(uint8_t* S, uint2 en, float a_sca
     *reinterpret_cast<unsigned short*>(S + off) = f16_term(__uint_as_float(en.y) * a_scale, term);
 }
 
-template <bool ATY, int NS>
+template <bool ATY, int NS, int NSB>
 __device__ __forceinline__ void tc_scatter_role(const uint2* __restrict__ entries, int64_t n_units, int a_terms, float a_scale,
                                                 uint8_t* sS, const uint8_t* sRing, const TcSlotMeta* sMeta, uint64_t* e_full,
-                                                uint64_t* e_free, uint64_t* s_full, uint64_t* s_free, int tid) {
+                                                uint64_t* e_free, uint64_t* s_full, uint64_t* s_free, int tid, int dbg = 0) {
     const int lane = tid & 31;
     const int grp = (tid >> 5) / TC_GROUP_WARPS;
     const int gt = tid - grp * TC_GROUP_THREADS;           // thread index inside the group
-    uint8_t* S = sS + grp * TC_S_BYTES;
     uint32_t lp = 0;                                        // passes this group has built so far
     uint32_t prev[TC_EPT];                                  // half-offsets this thread wrote for the previous unit (tile 0 | tile 1 << 16)
 #pragma unroll
@@ -756,12 +811,16 @@ __device__ __forceinline__ void tc_scatter_role(const uint2* __restrict__ entrie
         const uint2* sl0 = reinterpret_cast<const uint2*>(sRing + (size_t)slot * (2 * TC_SLOT_BYTES));
         const uint2* sl1 = reinterpret_cast<const uint2*>(sRing + (size_t)slot * (2 * TC_SLOT_BYTES) + TC_SLOT_BYTES);
         for (int term = 0; term < a_terms; term++, lp++) {
+            const uint32_t P = (uint32_t)s * (uint32_t)a_terms + (uint32_t)term;   // global pass index
+            const uint32_t sb = P % NSB, sb_use = P / NSB;
+            uint8_t* S = sS + sb * TC_S_BYTES;
             if (lane == 0) {
-                if (lp > 0) mbar_wait_crit(&s_free[grp], (lp - 1) & 1);     // the MMAs of this buffer's previous pass have retired
+                if (sb_use > 0) mbar_wait_crit(&s_free[sb], (sb_use - 1) & 1);   // the MMAs of this buffer's previous pass have retired
                 if (term == 0) mbar_wait(&e_full[slot], slot_use & 1);
             }
             __syncwarp();
-            if (!TC_UNSCATTER || (term == 0 && full_clear)) {
+            if (dbg & 1) {                                                   // (timing experiment: no clear)
+            } else if (!TC_UNSCATTER || (term == 0 && full_clear)) {
                 for (int i = gt; i < TC_S_BYTES / 16; i += TC_GROUP_THREADS) reinterpret_cast<uint4*>(S)[i] = make_uint4(0, 0, 0, 0);
             } else if (term == 0) {
 #pragma unroll
@@ -785,11 +844,13 @@ __device__ __forceinline__ void tc_scatter_role(const uint2* __restrict__ entrie
             }
             if (!TC_UNSCATTER || term == 0)
                 named_bar_sync(1 + grp, TC_GROUP_THREADS);   // every thread's clearing stores precede every scatter store
+            if (!(dbg & 8)) {                                                // (timing experiment: no scatter stores)
 #pragma unroll
             for (int k = 0; k < TC_EPT; k++) {
                 const int i = gt + k * TC_GROUP_THREADS;
                 if (i < m0) tc_scatter_one<ATY>(S, en0[k], a_scale, term);
                 if (i < m1) tc_scatter_one<ATY>(S, en1[k], a_scale, term);
+            }
             }
             if (n0 > lim || n1 > lim) {
                 // rare: a tile with more entries than the slot holds reads its tail from global memory
@@ -799,10 +860,10 @@ __device__ __forceinline__ void tc_scatter_role(const uint2* __restrict__ entrie
                     for (int i = lim + gt; i < n; i += TC_GROUP_THREADS) tc_scatter_one<ATY>(S, entries[e0 + i], a_scale, term);
                 }
             }
-            fence_proxy_async();
+            if (!(dbg & 16)) fence_proxy_async();                           // (timing experiment: no proxy fence)
             __syncwarp();
             if (lane == 0) {
-                mbar_arrive(&s_full[grp]);
+                mbar_arrive(&s_full[sb]);
                 if (term == a_terms - 1) mbar_arrive(&e_free[slot]);   // every lane of this warp has read the slot
             }
             if (TC_UNSCATTER && term == a_terms - 1) {
@@ -830,7 +891,7 @@ struct AxSmem {
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_ax_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ tile_ptr, int n_rb, int n_cb, int a_terms,
              float a_scale, int64_t nrows, const uint8_t* __restrict__ Xprep, const float* __restrict__ scales,
-             float* __restrict__ Y, const double* __restrict__ corr, unsigned* __restrict__ amax_out, int dbg) {
+             float* __restrict__ Y, const double* __restrict__ corr, unsigned* __restrict__ amax_out, int dbg, int pfd) {
     // (no integer round trip on this pointer: the compiler must keep seeing the shared address space, or every access
     // below becomes a generic LD/ST; the no-swizzle operand layouts only need 16 B alignment)
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -873,11 +934,12 @@ tc_ax_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ tile
     TcSeq seq{n_cb, false, n_mine, 0, 0, 0, 0, 0};
 
     if (warp < TC_SCATTER_WARPS) {
-        tc_scatter_role<false, AxSmem::NS>(entries, seq.n_units(), a_terms, a_scale, sS, sRing, sMeta, e_full, e_free, s_full,
-                                           s_free, tid);
+        tc_scatter_role<false, AxSmem::NS, TC_NSB>(entries, seq.n_units(), a_terms, a_scale, sS, sRing, sMeta, e_full, e_free, s_full,
+                                           s_free, tid, dbg);
     } else if (warp >= TC_W_ELOAD) {
+        tc_prefetch_prologue(entries, tile_ptr, seq, pfd, (warp - TC_W_ELOAD) * 32 + lane);
         if (lane == 0 && warp - TC_W_ELOAD < AxSmem::NS)
-            tc_entry_loader<AxSmem::NS>(entries, tile_ptr, seq, sRing, sMeta, e_full, e_free, warp - TC_W_ELOAD);
+            tc_entry_loader<AxSmem::NS>(entries, tile_ptr, seq, sRing, sMeta, e_full, e_free, warp - TC_W_ELOAD, pfd, dbg);
     } else if (warp == TC_W_BLOAD) {
         // ================= panel-slice loader =================
         if (lane == 0) {
@@ -913,20 +975,23 @@ tc_ax_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ tile
                     const int bb = it % AxSmem::NB;
                     mbar_wait(&d_full[bb], (it / AxSmem::NB) & 1);
                     TC_T(c_d);
-                    const int sb = it % TC_GROUPS;                           // unit `it` was built by scatter group sb
-                    const uint32_t lp0 = (it / TC_GROUPS) * (uint32_t)a_terms;
                     for (int term = 0; term < a_terms; term++) {
-                        mbar_wait_crit(&s_full[sb], (lp0 + term) & 1);
+                        const uint32_t P = it * (uint32_t)a_terms + (uint32_t)term;
+                        const uint32_t sb = P % TC_NSB;
+                        mbar_wait_crit(&s_full[sb], (P / TC_NSB) & 1);
                         tc_fence_after();
                         TC_T(c_s);
                         // K = 64: four K-steps; dense operand advances 2 chunks x 2048 B, sparse operand 2 x 4096 B
+                        if (!(dbg & 2))                                       // (timing experiment: no MMA)
                         umma_f16_run4(d_tmem, d_desc0 + (uint64_t)bb * (AxSmem::D_BYTES >> 4), s_desc0 + (uint64_t)sb * (TC_S_BYTES >> 4), idesc,
                                       (cb | term) != 0, 256, 512);
                         TC_T(c_issue);
-                        umma_commit(&s_free[sb]);
+                        if (dbg & 128) mbar_arrive(&s_free[sb]);             // (timing experiment with bit 2: plain arrive, no commit)
+                        else umma_commit(&s_free[sb]);
                         TC_T(c_commit);
                     }
-                    umma_commit(&d_free[bb]);
+                    if (dbg & 128) mbar_arrive(&d_free[bb]);
+                    else umma_commit(&d_free[bb]);
                 }
                 umma_commit(&acc_full[as]);
             }
@@ -1206,21 +1271,21 @@ struct AtySmem {
     static constexpr int NB = 2;
     static constexpr int NS = TC_ATY_NS_;                         // ring slots
     static constexpr int G = 8;                               // operator column blocks per CTA: 4 units x 128 TMEM columns
-    static constexpr int TOTAL = TC_NSB * TC_S_BYTES + NB * D_BYTES + NS * 2 * TC_SLOT_BYTES + 128;
+    static constexpr int TOTAL = TC_ATY_NSB * TC_S_BYTES + NB * D_BYTES + NS * 2 * TC_SLOT_BYTES + 128;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_aty_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ tile_ptr, int n_rb, int n_cb, int a_terms,
               float a_scale, int64_t n_eff, const uint8_t* __restrict__ Yprep, const float* __restrict__ scales,
-              float* __restrict__ Z, int n_groups, int rb_per_range) {
+              float* __restrict__ Z, int n_groups, int rb_per_range, int dbg, int pfd) {
     // (no integer round trip on this pointer: the compiler must keep seeing the shared address space, or every access
     // below becomes a generic LD/ST; the no-swizzle operand layouts only need 16 B alignment)
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint8_t* smem = smem_raw;
     uint8_t* sS = smem;
-    uint8_t* sD = sS + TC_NSB * TC_S_BYTES;
+    uint8_t* sD = sS + TC_ATY_NSB * TC_S_BYTES;
     uint8_t* sRing = sD + AtySmem::NB * AtySmem::D_BYTES;
-    __shared__ uint64_t s_full[TC_NSB], s_free[TC_NSB], d_full[AtySmem::NB], d_free[AtySmem::NB], acc_full;
+    __shared__ uint64_t s_full[TC_ATY_NSB], s_free[TC_ATY_NSB], d_full[AtySmem::NB], d_free[AtySmem::NB], acc_full;
     __shared__ uint64_t e_full[AtySmem::NS], e_free[AtySmem::NS];
     __shared__ TcSlotMeta sMeta[AtySmem::NS];
     __shared__ uint32_t s_tmem;
@@ -1235,7 +1300,7 @@ tc_aty_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ til
     const int n_units = (ntr + 1) / 2;
 
     if (tid == 0) {
-        for (int i = 0; i < TC_NSB; i++) {
+        for (int i = 0; i < TC_ATY_NSB; i++) {
             mbar_init(&s_full[i], TC_GROUP_WARPS);
             mbar_init(&s_free[i], 1);
         }
@@ -1260,11 +1325,12 @@ tc_aty_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ til
 
     if (warp < TC_SCATTER_WARPS) {
         if (active)
-            tc_scatter_role<true, AtySmem::NS>(entries, seq.n_units(), a_terms, a_scale, sS, sRing, sMeta, e_full, e_free, s_full,
-                                               s_free, tid);
+            tc_scatter_role<true, AtySmem::NS, TC_ATY_NSB>(entries, seq.n_units(), a_terms, a_scale, sS, sRing, sMeta, e_full, e_free, s_full,
+                                               s_free, tid, dbg);
     } else if (warp >= TC_W_ELOAD) {
+        if (active) tc_prefetch_prologue(entries, tile_ptr, seq, pfd, (warp - TC_W_ELOAD) * 32 + lane);
         if (active && lane == 0 && warp - TC_W_ELOAD < AtySmem::NS)
-            tc_entry_loader<AtySmem::NS>(entries, tile_ptr, seq, sRing, sMeta, e_full, e_free, warp - TC_W_ELOAD);
+            tc_entry_loader<AtySmem::NS>(entries, tile_ptr, seq, sRing, sMeta, e_full, e_free, warp - TC_W_ELOAD, pfd, dbg);
     } else if (warp == TC_W_BLOAD) {
         if (lane == 0 && active) {
             uint32_t it = 0;
@@ -1272,6 +1338,7 @@ tc_aty_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ til
                 const int bb = it % AtySmem::NB;
                 const uint32_t use = it / AtySmem::NB;
                 if (use > 0) mbar_wait(&d_free[bb], (use - 1) & 1);
+                if (dbg & 4) { mbar_arrive(&d_full[bb]); continue; }        // (timing experiment: no panel loads)
                 mbar_expect_tx(&d_full[bb], AtySmem::D_BYTES);
                 bulk_g2s(sD + bb * AtySmem::D_BYTES, Yprep + (size_t)rb * AtySmem::D_BYTES, AtySmem::D_BYTES, &d_full[bb]);
             }
@@ -1286,16 +1353,18 @@ tc_aty_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ til
                 mbar_wait(&d_full[bb], (it / AtySmem::NB) & 1);
                 for (int u = 0; u < n_units; u++, unit++) {
                     const uint32_t d_tmem = tmem_base + (uint32_t)u * 128u;
-                    const int sb = unit % TC_GROUPS;                         // built by scatter group sb
-                    const uint32_t lp0 = (unit / TC_GROUPS) * (uint32_t)a_terms;
                     for (int term = 0; term < a_terms; term++) {
-                        mbar_wait_crit(&s_full[sb], (lp0 + term) & 1);
+                        const uint32_t P = unit * (uint32_t)a_terms + (uint32_t)term;
+                        const uint32_t sb = P % TC_ATY_NSB;
+                        mbar_wait_crit(&s_full[sb], (P / TC_ATY_NSB) & 1);
                         tc_fence_after();
                         // K = 128 rows: eight K-steps, both operands advance 2 chunks x 2048 B per step
                         const uint64_t dd = d_desc0 + (uint64_t)bb * (AtySmem::D_BYTES >> 4);
                         const uint64_t sd = s_desc0 + (uint64_t)sb * (TC_S_BYTES >> 4);
+                        if (!(dbg & 2)) {                                     // (timing experiment: no MMA)
                         umma_f16_run4(d_tmem, dd, sd, idesc, ((rb - rb0) | term) != 0, 256, 256);
                         umma_f16_run4(d_tmem, dd + 1024, sd + 1024, idesc, 1, 256, 256);
+                        }
                         umma_commit(&s_free[sb]);
                     }
                 }
@@ -1341,6 +1410,13 @@ __global__ void tc_init_z_kernel(float* __restrict__ Z, int64_t n_eff, const flo
 
 bool tc_enabled(const salg_ctx* ctx) { return ctx->spmm_impl == 0; }
 
+// L2 prefetch distance of the entry lists, in units (SALG_TC_PFD overrides; 0 = off)
+static int tc_pfd() {
+    const char* e = getenv("SALG_TC_PFD");
+    const int v = e ? atoi(e) : 8;      // (measured: 8-16 units ahead -1..2 %, 32 and more +1 %; the ring is not the limit)
+    return v < 0 ? 0 : v;
+}
+
 static TcTiles* tiles_of(salg_ctx* ctx, const salg_csr* c) {
     if (!c->tc) c->tc = tc_build<float>(ctx, c);
     return (TcTiles*)c->tc;
@@ -1372,8 +1448,10 @@ static void tc_dbg_print(salg_ctx* ctx, const char* what) {
     unsigned long long h[32];
     cudaStreamSynchronize(ctx->stream);
     cudaMemcpyFromSymbol(h, g_tc_dbg, sizeof(h));
-    fprintf(stderr, "[tc %s] scatter total %llu passes %llu: s_free %llu zero %llu bar %llu e_full %llu scatter %llu fence %llu arrive %llu e_free %llu\n",
-            what, h[0], h[9], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8]);
+    fprintf(stderr, "[tc %s] scatter(grp 0) total %llu passes %llu: wait s_free %llu wait e_full %llu clear+loads %llu bar %llu scatter %llu fence %llu | loader0 wait e_free %llu over %llu units\n",
+            what, h[0], h[9], h[1], h[2], h[3], h[4], h[5], h[6], h[20], h[21]);
+    unsigned long long z[32] = {0};
+    cudaMemcpyToSymbol(g_tc_dbg, z, sizeof(z));
     fprintf(stderr, "[tc %s] mma total %llu: acc_free %llu d_full %llu s_full %llu issue %llu commit %llu | epilogue wait %llu work %llu\n", what,
             h[10], h[11], h[12], h[13], h[14], h[15], h[16], h[17]);
 }
@@ -1395,7 +1473,7 @@ void tc_spmm_A(salg_ctx* ctx, const salg_csr* c, const float* X, float* Y, const
     int grid = n_pairs < ctx->sm_count ? n_pairs : ctx->sm_count;
     tc_ax_kernel<<<grid, TC_THREADS, AxSmem::TOTAL, st>>>(t->entries, t->tile_ptr, t->n_rb, t->n_cb, t->a_terms, t->a_scale,
                                                           c->nrows, Xprep.get(), scales.get(), Y, corr, d_amax,
-                                                          getenv("SALG_TC_DBG") ? atoi(getenv("SALG_TC_DBG")) : 0);
+                                                          getenv("SALG_TC_DBG") ? atoi(getenv("SALG_TC_DBG")) : 0, tc_pfd());
     ctx->n_launch++;
     SALG_CUDA(cudaGetLastError());
     tc_dbg_print(ctx, "ax");
@@ -1516,9 +1594,11 @@ static void tc_aty_launch(salg_ctx* ctx, const salg_csr* c, TcTiles* t, const ui
     set_max_dyn_smem(tc_aty_kernel, (int)(AtySmem::TOTAL));
     tc_aty_kernel<<<n_groups * ranges, TC_THREADS, AtySmem::TOTAL, st>>>(t->entries, t->tile_ptr, n_rb_real, t->n_cb, t->a_terms,
                                                                          t->a_scale, c->ncols, Yprep, scales, Z,
-                                                                         n_groups, rb_per_range);
+                                                                         n_groups, rb_per_range,
+                                                                         getenv("SALG_TC_DBG") ? atoi(getenv("SALG_TC_DBG")) : 0, tc_pfd());
     ctx->n_launch++;
     SALG_CUDA(cudaGetLastError());
+    tc_dbg_print(ctx, "aty");
 }
 
 }  // namespace salg

@@ -117,6 +117,19 @@ def row_meta(spec: SynthSpec, rows):
     return cluster, sf
 
 
+def expected_row_nnz(spec: SynthSpec, row0: int, row1: int):
+    """Expected stored entries of rows [row0, row1) under the generator's model (f64): a row's (cluster, size-factor)
+    pair fixes its per-gene Poisson levels.  Used to cut row shards balanced by entries without
+    generating the matrix."""
+    p_nz = 1.0 - spec.cdf[:, 0].astype(np.float64) / 4294967296.0
+    table = np.empty((spec.n_clusters, N_SF), dtype=np.float64)
+    for sf in range(N_SF):
+        lvl = np.clip(spec.base_level.astype(np.int64) + int(spec.sf_offset[sf]), 0, N_LEVELS - 1)
+        table[:, sf] = p_nz[lvl].sum(axis=1)
+    cluster, sf = row_meta(spec, np.arange(row0, row1, dtype=np.uint64))
+    return table[cluster, sf]
+
+
 def generate_rows(spec: SynthSpec, row0: int, row1: int, dtype=np.float32, block=512):
     """CSR (indptr, indices[int64], data[dtype]) of rows [row0, row1) of the spec's matrix."""
     indptr = [0]
