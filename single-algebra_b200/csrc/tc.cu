@@ -82,6 +82,18 @@ constexpr int TC_S_BYTES = 32768;     // sparse operand buffer: 256 x 64 (A X) o
 #ifndef TC_ATY_NSB_
 #define TC_ATY_NSB_ 3
 #endif
+#ifndef TC_OCC_
+#define TC_OCC_ 1
+#endif
+#ifndef TC_ATY_OCC_
+#define TC_ATY_OCC_ 1
+#endif
+constexpr int TC_OCC = TC_OCC_;       // CTAs per SM (A X): 2 halves every per-CTA resource (TMEM 256 columns: one accumulator
+                                      // stage) and lets two independent pipelines hide each other's hand-off latencies
+constexpr int TC_ATY_OCC = TC_ATY_OCC_;   // the same for A^T Y (4 operator column blocks per CTA instead of 8)
+constexpr int TC_ACC = TC_OCC == 1 ? 2 : 1;          // A X accumulator stages
+constexpr int TC_TMEM_COLS = 512 / TC_OCC;
+constexpr int TC_ATY_TMEM_COLS = 512 / TC_ATY_OCC;
 constexpr int TC_NSB = TC_NSB_;       // sparse operand buffers (A X): pass P (unit * terms + term) uses buffer P % NSB
 constexpr int TC_ATY_NSB = TC_ATY_NSB_;   // the same for A^T Y (its dense stages are twice as large)
 constexpr int TC_EPT = (TC_SLOT_ENTRIES + TC_GROUP_THREADS - 1) / TC_GROUP_THREADS;   // ring entries per thread and tile
@@ -888,7 +900,7 @@ struct AxSmem {
     static constexpr int TOTAL = TC_NSB * TC_S_BYTES + NB * D_BYTES + NS * 2 * TC_SLOT_BYTES + 128;
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, TC_OCC)
 tc_ax_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ tile_ptr, int n_rb, int n_cb, int a_terms,
              float a_scale, int64_t nrows, const uint8_t* __restrict__ Xprep, const float* __restrict__ scales,
              float* __restrict__ Y, const double* __restrict__ corr, unsigned* __restrict__ amax_out, int dbg, int pfd) {
@@ -899,7 +911,7 @@ tc_ax_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ tile
     uint8_t* sS = smem;
     uint8_t* sD = sS + TC_NSB * TC_S_BYTES;
     uint8_t* sRing = sD + AxSmem::NB * AxSmem::D_BYTES;
-    __shared__ uint64_t s_full[TC_NSB], s_free[TC_NSB], d_full[AxSmem::NB], d_free[AxSmem::NB], acc_full[2], acc_free[2];
+    __shared__ uint64_t s_full[TC_NSB], s_free[TC_NSB], d_full[AxSmem::NB], d_free[AxSmem::NB], acc_full[TC_ACC], acc_free[TC_ACC];
     __shared__ uint64_t e_full[AxSmem::NS], e_free[AxSmem::NS];
     __shared__ TcSlotMeta sMeta[AxSmem::NS];
     __shared__ uint32_t s_tmem;
@@ -912,7 +924,7 @@ tc_ax_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ tile
             mbar_init(&s_full[i], TC_GROUP_WARPS);
             mbar_init(&s_free[i], 1);
         }
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < TC_ACC; i++) {
             mbar_init(&acc_full[i], 1);
             mbar_init(&acc_free[i], 4);
         }
@@ -926,7 +938,7 @@ tc_ax_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ tile
         }
         fence_barrier_init();
     }
-    if (warp == 0) tmem_alloc(&s_tmem, 512);
+    if (warp == 0) tmem_alloc(&s_tmem, TC_TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -966,8 +978,8 @@ tc_ax_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ tile
             constexpr uint32_t idesc = tc_idesc(256);
             long long c_acc = 0, c_d = 0, c_s = 0, c_issue = 0, c_commit = 0, t_prev = clock64(), t_begin = t_prev;
             for (int gi = 0; gi < n_mine; gi++) {
-                const int as = gi & 1;
-                if (gi >= 2) mbar_wait(&acc_free[as], ((gi >> 1) - 1) & 1);
+                const int as = gi % TC_ACC;
+                if (gi >= TC_ACC) mbar_wait(&acc_free[as], ((gi / TC_ACC) - 1) & 1);
                 tc_fence_after();
                 TC_T(c_acc);
                 const uint32_t d_tmem = tmem_base + (uint32_t)as * 256u;
@@ -1009,8 +1021,8 @@ tc_ax_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ tile
         long long c_wait = 0, c_work = 0, t_prev = clock64();
         float amax = 0.f;                       // max |Y| of this thread's outputs (scale of the next pre-split)
         for (int gi = 0; gi < n_mine; gi++) {
-            const int as = gi & 1;
-            mbar_wait_warp(&acc_full[as], (gi >> 1) & 1, lane);
+            const int as = gi % TC_ACC;
+            mbar_wait_warp(&acc_full[as], (gi / TC_ACC) & 1, lane);
             tc_fence_after();
             TC_T(c_wait);
             const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)gi * gridDim.x) * 256;
@@ -1044,7 +1056,7 @@ tc_ax_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ tile
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, 512);
+    if (warp == 0) tmem_dealloc(tmem_base, TC_TMEM_COLS);
 }
 
 // ---- fused Gram + pre-split of a tall panel ---------------------------------------------------------------------------------
@@ -1270,11 +1282,11 @@ struct AtySmem {
     static constexpr int D_BYTES = 128 * TC_RB * 2;          // 32 KB per stage: Y row block (M = 128) x (K = 128 rows)
     static constexpr int NB = 2;
     static constexpr int NS = TC_ATY_NS_;                         // ring slots
-    static constexpr int G = 8;                               // operator column blocks per CTA: 4 units x 128 TMEM columns
+    static constexpr int G = 8 / TC_ATY_OCC;                      // operator column blocks per CTA: G / 2 units x 128 TMEM columns
     static constexpr int TOTAL = TC_ATY_NSB * TC_S_BYTES + NB * D_BYTES + NS * 2 * TC_SLOT_BYTES + 128;
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, TC_ATY_OCC)
 tc_aty_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ tile_ptr, int n_rb, int n_cb, int a_terms,
               float a_scale, int64_t n_eff, const uint8_t* __restrict__ Yprep, const float* __restrict__ scales,
               float* __restrict__ Z, int n_groups, int rb_per_range, int dbg, int pfd) {
@@ -1315,7 +1327,7 @@ tc_aty_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ til
         mbar_init(&acc_full, 1);
         fence_barrier_init();
     }
-    if (warp == 0) tmem_alloc(&s_tmem, 512);
+    if (warp == 0) tmem_alloc(&s_tmem, TC_ATY_TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -1398,7 +1410,7 @@ tc_aty_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ til
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, 512);
+    if (warp == 0) tmem_dealloc(tmem_base, TC_ATY_TMEM_COLS);
 }
 
 // Z[r][j] = -mu[r] * cs[j]  (or 0)
@@ -1470,7 +1482,7 @@ void tc_spmm_A(salg_ctx* ctx, const salg_csr* c, const float* X, float* Y, const
     if (d_amax) SALG_CUDA(cudaMemsetAsync(d_amax, 0, 4, st));
     set_max_dyn_smem(tc_ax_kernel, (int)(AxSmem::TOTAL));
     int n_pairs = t->n_rb / 2;
-    int grid = n_pairs < ctx->sm_count ? n_pairs : ctx->sm_count;
+    int grid = n_pairs < ctx->sm_count * TC_OCC ? n_pairs : ctx->sm_count * TC_OCC;
     tc_ax_kernel<<<grid, TC_THREADS, AxSmem::TOTAL, st>>>(t->entries, t->tile_ptr, t->n_rb, t->n_cb, t->a_terms, t->a_scale,
                                                           c->nrows, Xprep.get(), scales.get(), Y, corr, d_amax,
                                                           getenv("SALG_TC_DBG") ? atoi(getenv("SALG_TC_DBG")) : 0, tc_pfd());
@@ -1586,7 +1598,7 @@ static void tc_aty_launch(salg_ctx* ctx, const salg_csr* c, TcTiles* t, const ui
     cudaStream_t st = ctx->stream;
     int n_groups = (int)ceil_div(t->n_cb, AtySmem::G);
     int n_rb_real = (int)ceil_div(c->nrows, TC_RB);
-    int ranges = ctx->sm_count / n_groups;
+    int ranges = ctx->sm_count * TC_ATY_OCC / n_groups;
     if (ranges < 1) ranges = 1;
     if (ranges > n_rb_real) ranges = n_rb_real;
     int rb_per_range = (int)ceil_div(n_rb_real, ranges);
