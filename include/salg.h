@@ -22,6 +22,10 @@
  *    not safe for concurrent calls; one process per GPU in multi-GPU runs (rows sharded).
  *  - there is no CPU fallback: without a CUDA device every compute entry point fails with
  *    SALG_ERR_CUDA.
+ *  - per-GPU size limits: row offsets are 64-bit everywhere, so statistics, Normalize / Log1P, column selection, transform
+ *    and the fused masked fit (which only ever tiles the KEPT entries) take shards of any size that fits in memory; the tile
+ *    format and the transposed copy index entries with 32 bits, so unmasked f32 fits, f64 fits and Lanczos fits need
+ *    < 2^31 stored entries PER GPU SHARD (SALG_ERR_UNSUPPORTED otherwise: shard the rows over more GPUs).
  */
 #ifndef SALG_H
 #define SALG_H
@@ -241,6 +245,17 @@ int salg_pca_fit_f32(salg_ctx* ctx, const salg_csr* x, const salg_pca_params* pa
 int salg_pca_fit_f64(salg_ctx* ctx, const salg_csr* x, const salg_pca_params* params,
                      const uint8_t* mask, int64_t mask_len,
                      const double* omega, int64_t omega_rows, int64_t omega_cols, salg_pca** out);
+/* The same fit straight from a HOST matrix in the AnnData / scipy layout (int64 offsets, int32 column indices, f32
+ * values).  A masked randomized fit STREAMS the matrix: row chunks cross PCIe once, double-buffered, and go
+ * through validation + the statistics / mask-compaction pass while the next chunk uploads; only the kept entries and the
+ * tile format stay on the device (a 16.8 GB matrix needs ~3 GB).  Pinned host memory gives the overlap; pageable memory
+ * works but serialises.  Other configurations (no mask, Lanczos, values that are not raw counts in rows too dense for the
+ * kept-entry slots) upload the matrix, fit and free it inside the call.  Replaces the upload + fit pair of
+ * MaskedSparsePCA::fit (pca/sparse_masked/mod.rs:255-419) for host-resident inputs. */
+int salg_pca_fit_host_f32(salg_ctx* ctx, int64_t nrows, int64_t ncols, int64_t nnz, const int64_t* row_offsets,
+                          const int32_t* col_indices, const float* values, const salg_pca_params* params,
+                          const uint8_t* mask, int64_t mask_len, const float* omega, int64_t omega_rows,
+                          int64_t omega_cols, salg_pca** out);
 int salg_pca_free(salg_pca* pca);
 /* d = number of components returned, n_eff = kept columns, ncols = full column count */
 int salg_pca_dims(const salg_pca* pca, int64_t* d, int64_t* n_eff, int64_t* ncols, int* dtype);

@@ -99,6 +99,7 @@ PROTOTYPES = {
     "salg_preprocess_f64": [_P, _P, C.c_double, _P, _P],
     "salg_pca_params_default": [C.POINTER(PcaParams)],
     "salg_pca_fit_f32": [_P, _P, C.POINTER(PcaParams), _P, _i64, _P, _i64, _i64, C.POINTER(_P)],
+    "salg_pca_fit_host_f32": [_P, _i64, _i64, _i64, _P, _P, _P, C.POINTER(PcaParams), _P, _i64, _P, _i64, _i64, C.POINTER(_P)],
     "salg_pca_fit_f64": [_P, _P, C.POINTER(PcaParams), _P, _i64, _P, _i64, _i64, C.POINTER(_P)],
     "salg_pca_free": [_P],
     "salg_pca_dims": [_P, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_int)],

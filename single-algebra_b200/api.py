@@ -550,8 +550,37 @@ class _PCABase:
         except Exception:
             pass
 
+    def _fit_host(self, x, omega, keep_scores, fetch=True):
+        """Host-resident `CsrMatrix` (int32 indices, f32): `salg_pca_fit_host_f32` — a masked randomized fit streams the
+        matrix through the statistics + compaction pass while it uploads."""
+        lib = N.load()
+        ctx = x.ctx
+        mask_arr, mask_len = None, 0
+        if self._masked:
+            mask_arr = np.ascontiguousarray(self.mask.astype(np.uint8))
+            mask_len = len(mask_arr)
+        om, orows, ocols = None, 0, 0
+        if omega is not None:
+            om = np.ascontiguousarray(omega, dtype=np.float32)
+            orows, ocols = om.shape
+        p = self._params(keep_scores)
+        h = C.c_void_p()
+        self._free_model()
+        N.check(lib.salg_pca_fit_host_f32(ctx._h, x.nrows, x.ncols, x.nnz, N.ptr(x.row_offsets.view(np.int64)),
+                                          N.ptr(x.col_indices), N.ptr(x.values), C.byref(p), N.ptr(mask_arr), mask_len,
+                                          N.ptr(om), orows, ocols, C.byref(h)))
+        self._model = h
+        self._dtype = np.dtype(np.float32)
+        self._ctx = ctx
+        if fetch:
+            self._fetch()
+        return self
+
     def _fit(self, x, omega, keep_scores, fetch=True):
         lib = N.load()
+        if (isinstance(x, CsrMatrix) and x._dev is None and x.dtype == np.float32 and x.col_indices.dtype == np.int32
+                and self._masked and self.svdmethod.kind == N.SVD_RANDOM):
+            return self._fit_host(x, omega, keep_scores, fetch)
         d = _as_device(x)
         sfx = "f64" if d.dtype == np.float64 else "f32"
         mask_arr, mask_len = None, 0
@@ -640,10 +669,10 @@ class _PCABase:
         self._fit(x, omega, keep_scores=True)
         lib = N.load()
         sfx = "f64" if self._dtype == np.float64 else "f32"
-        d = _as_device(x)
+        nrows = x.nrows
         if out is None:
-            out = np.empty((d.nrows, self.components_.shape[0]), self._dtype)
-        assert out.shape == (d.nrows, self.components_.shape[0]) and out.dtype == self._dtype
+            out = np.empty((nrows, self.components_.shape[0]), self._dtype)
+        assert out.shape == (nrows, self.components_.shape[0]) and out.dtype == self._dtype
         N.check(getattr(lib, f"salg_pca_fit_scores_{sfx}")(self._ctx._h, self._model, N.ptr(out)))   # `out` may be pinned
         return out
 

@@ -262,6 +262,9 @@ template <typename T> void csr_ensure_transpose(salg_ctx* ctx, const salg_csr* c
 template <typename T> salg_csr* csr_select_columns(salg_ctx* ctx, const salg_csr* c, const uint8_t* mask_host,
                                                    int64_t* d_row_kept = nullptr);
 void exclusive_scan_i64(salg_ctx* ctx, const int64_t* in, int64_t* out, int64_t n);
+salg_csr* csr_upload_i32_f32(salg_ctx* ctx, int64_t nrows, int64_t ncols, int64_t nnz, const int64_t* off, const int32_t* idx,
+                             const float* val);
+salg_csr* csr_shell_from_host_offsets(salg_ctx* ctx, int dtype, int64_t nrows, int64_t ncols, int64_t nnz, const int64_t* h_off);
 
 // ---- stats.cu -------------------------------------------------------------------------------------
 // column sums / sums of squares / stored-entry counts in f64 on the device (zeroed here; all-reduced
@@ -273,6 +276,12 @@ template <typename T> void col_stats_device(salg_ctx* ctx, const salg_csr* c, do
                                             int64_t n_kept = 0, uint32_t* kept_col = nullptr, void* kept_val = nullptr,
                                             int kept_shift = 0, int* kept_overflow = nullptr);
 bool col_stats_can_fuse_compaction(const salg_csr* c, int64_t n_kept);
+// streamed fits (pca.cu): the masked statistics + fused compaction pass over one staged row chunk, see stats.cu
+bool col_stats_probe_int_f32(salg_ctx* ctx, cudaStream_t st, const float* d_val, int64_t n, int* d_flag1);
+void col_stats_masked_chunk_f32(salg_ctx* ctx, cudaStream_t st, const int64_t* ptr, const uint32_t* col, const float* val,
+                                int64_t nrows, int64_t ncols, int64_t n_kept, double* d_sum, double* d_sumsq,
+                                const uint32_t* keepbits, int64_t* row_kept, uint32_t* kept_col, float* kept_val, int kept_shift,
+                                int* flags, bool intsum);
 template <typename T> void sum_row_device(salg_ctx* ctx, const salg_csr* c, T* d_out);
 int64_t global_nrows(salg_ctx* ctx, int64_t local_rows);
 

@@ -179,6 +179,46 @@ static salg_csr* csr_upload(salg_ctx* ctx, int64_t nrows, int64_t ncols, int64_t
     return c;
 }
 
+// helpers for the streamed fit (pca.cu)
+salg_csr* csr_upload_i32_f32(salg_ctx* ctx, int64_t nrows, int64_t ncols, int64_t nnz, const int64_t* off, const int32_t* idx,
+                             const float* val) {
+    return csr_upload<float, int64_t, uint32_t>(ctx, nrows, ncols, nnz, off, (const uint32_t*)idx, val);
+}
+// "shell" of a host-resident matrix: validated row offsets on the device, no entry arrays
+salg_csr* csr_shell_from_host_offsets(salg_ctx* ctx, int dtype, int64_t nrows, int64_t ncols, int64_t nnz, const int64_t* h_off) {
+    SALG_REQUIRE(ctx && h_off, SALG_ERR_BAD_ARG, "ctx/row_offsets is NULL");
+    SALG_REQUIRE(nrows >= 0 && ncols >= 0 && nnz >= 0, SALG_ERR_BAD_ARG, "negative dimension");
+    SALG_REQUIRE(ncols < (int64_t)0xFFFFFFFFLL, SALG_ERR_BAD_ARG, "ncols must fit 32 bits on the device");
+    SALG_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    salg_csr* c = new salg_csr();
+    c->ctx = ctx;
+    c->dtype = dtype;
+    c->nrows = nrows;
+    c->ncols = ncols;
+    c->nnz = nnz;
+    try {
+        c->row_ptr = (int64_t*)dev_alloc(ctx, (size_t)(nrows + 1) * 8);
+        DevBuf<int64_t> tmp((size_t)nrows + 1, st);
+        DevBuf<int> flag(1, st);
+        SALG_CUDA(cudaMemsetAsync(flag.get(), 0, 4, st));
+        SALG_CUDA(cudaMemcpyAsync(tmp.get(), h_off, (size_t)(nrows + 1) * 8, cudaMemcpyHostToDevice, st));
+        copy_offsets_kernel<int64_t><<<(unsigned)ceil_div(nrows + 1, 256), 256, 0, st>>>(tmp.get(), c->row_ptr, nrows + 1, nnz,
+                                                                                        flag.get());
+        ctx->n_launch++;
+        SALG_CUDA(cudaGetLastError());
+        int h = 0;
+        SALG_CUDA(cudaMemcpyAsync(&h, flag.get(), 4, cudaMemcpyDeviceToHost, st));
+        SALG_CUDA(cudaStreamSynchronize(st));
+        if (h) throw Error(SALG_ERR_BAD_ARG, "invalid CSR: row offsets must start at 0, be non-decreasing and end at nnz");
+    } catch (...) {
+        cudaStreamSynchronize(st);
+        csr_destroy(c);
+        throw;
+    }
+    return c;
+}
+
 __global__ void widen_idx_kernel(const uint32_t* __restrict__ src, uint64_t* __restrict__ dst, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;

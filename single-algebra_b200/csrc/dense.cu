@@ -94,29 +94,31 @@ template void panel_gram<float>(salg_ctx*, const float*, int64_t, double*);
 template void panel_gram<double>(salg_ctx*, const double*, int64_t, double*);
 
 // ---- Cholesky G = L L^T of the leading k x k block, R = L^T and R^{-1}; one CTA of 512 threads ----------------------
-// This kernel is replicated on every GPU of a row-sharded run and runs ~25 times per fit, so its latency is serial
-// time at any GPU count (the first version, one thread per row with the row in registers, took 92 us per call).
-// Here the matrix lives in shared memory and every elimination step is ONE block-wide rank-1 update behind ONE
-// barrier: step j updates the trailing block of A (columns > j) and, in the same sweep, the forward substitution of
-// the identity (columns <= j of B), so L^{-1} falls out of the same 64 steps.  Column j of A is left UNSCALED
-// (readers multiply by 1/l_jj), which is what removes the second barrier of the textbook loop.
-// Thread (g, c): column c, rows g, g + 8, ..., g + 56.  Pivots that are not safely positive are floored
-// (rank-deficient panels: l > rank(A)); flag bit 1 is raised, the caller's second CholeskyQR pass re-orthonormalises.
+// This kernel is replicated on every GPU of a row-sharded run and runs ~18 times per fit, so its latency is serial
+// time at any GPU count (first version, one thread per row: 92 us per call; second, one block-wide rank-1 update and one
+// barrier per column: 35 us).  This version is BLOCKED by 8 columns: per block (1) one warp factors the 8 x 8 diagonal
+// block in registers (the pivot chain — shuffle, rsqrt, 7 fused multiply-adds per column — is the only serial part left)
+// and inverts it, (2) 8-term triangular products give the panel below and the block row of L^{-1} (forward substitution of
+// the identity, carried along), (3) ONE block-wide rank-8 update of the trailing matrix and of the rows of L^{-1} below.
+// 8 x 3 barriers instead of 64.  The matrix is padded with the identity to 64 x 64, so every block is full.
+// Pivots that are not safely positive are floored (rank-deficient panels: l > rank(A)); flag bit 1 is raised, the
+// caller's second CholeskyQR pass re-orthonormalises.
 constexpr int CHOL_THREADS = 512;
 constexpr int CHOL_LD = LP + 1;
-constexpr size_t CHOL_SMEM = (size_t)(2 * LP * CHOL_LD + 2 * LP + 2) * sizeof(double);
+constexpr int CHOL_NB = 8;
+constexpr size_t CHOL_SMEM = (size_t)(2 * LP * CHOL_LD + 2 * CHOL_NB * (CHOL_NB + 1) + 2) * sizeof(double);
 
 template <typename T>
 __global__ void __launch_bounds__(CHOL_THREADS)
 chol_inv_kernel(const double* __restrict__ G, int k, double* __restrict__ R, double* __restrict__ Rinv,
                 T* __restrict__ RinvT, int* __restrict__ flag) {
     extern __shared__ double chol_sm[];
-    double* A = chol_sm;                       // [64][65] lower triangle: trailing matrix, later unscaled columns of L
-    double* B = A + LP * CHOL_LD;              // [64][65] forward-substituted identity, later unscaled rows of L^{-1}
-    double* dinv = B + LP * CHOL_LD;           // 1 / l_jj
-    double* ldiag = dinv + LP;                 // l_jj
-    double* s_md = ldiag + LP;                 // [2]
-    const int tid = threadIdx.x;
+    double* A = chol_sm;                       // [64][65] lower triangle: trailing matrix, finished columns hold L
+    double* B = A + LP * CHOL_LD;              // [64][65] forward-substituted identity, finished rows hold L^{-1}
+    double* L8 = B + LP * CHOL_LD;             // [8][9] diagonal block of L
+    double* Li8 = L8 + CHOL_NB * (CHOL_NB + 1);   // [8][9] its inverse
+    double* s_md = Li8 + CHOL_NB * (CHOL_NB + 1); // [2]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c = tid & 63, g = tid >> 6;
 #pragma unroll
     for (int m = 0; m < 8; m++) {
@@ -134,45 +136,113 @@ chol_inv_kernel(const double* __restrict__ G, int k, double* __restrict__ R, dou
     const double mdiag = fmax(s_md[0], s_md[1]);
     const double floor_piv = (mdiag > 0.0 ? mdiag : 1.0) * 1e-13;
     bool bad = false;
-    for (int j = 0; j < k; j++) {
-        double p = A[j * CHOL_LD + j];
-        if (!(p > floor_piv)) {
-            p = floor_piv;
-            bad = true;
-        }
-        const double di = rsqrt(p);
-        if (tid == 0) {
-            dinv[j] = di;
-            ldiag[j] = p * di;
-        }
-        // the row-j factors this thread needs: l_cj (trailing update) or (L^{-1})_jc (substitution), both scaled once
-        const double rowj = ((c > j) ? A[c * CHOL_LD + j] : B[j * CHOL_LD + c]) * di;
-        double* M = (c > j) ? A : B;
+    for (int j0 = 0; j0 < LP; j0 += CHOL_NB) {
+        // ---- (1) diagonal block: lane r (mod 8) holds row r of the block
+        if (warp == 0) {
+            const int r = lane & 7;
+            double a[CHOL_NB], di[CHOL_NB];
 #pragma unroll
-        for (int m = 0; m < 8; m++) {
-            const int t = g + 8 * m;
-            if (t > j && (c <= j || c <= t)) {
-                const double ltj = A[t * CHOL_LD + j] * di;
-                M[t * CHOL_LD + c] = fma(-ltj, rowj, M[t * CHOL_LD + c]);
+            for (int cc = 0; cc < CHOL_NB; cc++) a[cc] = A[(j0 + r) * CHOL_LD + j0 + cc];
+#pragma unroll
+            for (int j = 0; j < CHOL_NB; j++) {
+                double p = __shfl_sync(0xFFFFFFFFu, a[j], j);
+                if (!(p > floor_piv)) {
+                    p = floor_piv;
+                    bad = true;
+                }
+                const double d = rsqrt(p);
+                di[j] = d;
+                a[j] = (r == j) ? p * d : a[j] * d;          // column j of L (rows >= j)
+#pragma unroll
+                for (int cc = j + 1; cc < CHOL_NB; cc++) {
+                    const double lc = __shfl_sync(0xFFFFFFFFu, a[j], cc);
+                    if (r >= cc) a[cc] = fma(-a[j], lc, a[cc]);
+                }
+            }
+            if (lane < CHOL_NB) {
+#pragma unroll
+                for (int cc = 0; cc < CHOL_NB; cc++) L8[r * (CHOL_NB + 1) + cc] = (cc <= r) ? a[cc] : 0.0;
+            }
+            __syncwarp();
+            if (lane < CHOL_NB) {           // column `lane` of the inverse by forward substitution
+                const int cc = lane;
+                double x[CHOL_NB];
+#pragma unroll
+                for (int t = 0; t < CHOL_NB; t++) {
+                    double sacc = 0.0;
+#pragma unroll
+                    for (int m = 0; m < t; m++) sacc = fma(L8[t * (CHOL_NB + 1) + m], x[m], sacc);
+                    x[t] = (t < cc) ? 0.0 : ((t == cc) ? di[t] : -sacc * di[t]);
+                    Li8[t * (CHOL_NB + 1) + cc] = x[t];
+                }
+            }
+        }
+        __syncthreads();
+        // ---- (2) panel below the block (threads 0-63: one row each), the block itself (64-127), block row of L^{-1} (128-191)
+        if (tid < 64) {
+            const int t = tid;
+            if (t >= j0 + CHOL_NB) {
+                double a[CHOL_NB];
+#pragma unroll
+                for (int b = 0; b < CHOL_NB; b++) a[b] = A[t * CHOL_LD + j0 + b];
+#pragma unroll
+                for (int aa = 0; aa < CHOL_NB; aa++) {
+                    double sacc = 0.0;
+#pragma unroll
+                    for (int b = 0; b <= aa; b++) sacc = fma(a[b], Li8[aa * (CHOL_NB + 1) + b], sacc);
+                    A[t * CHOL_LD + j0 + aa] = sacc;
+                }
+            }
+        } else if (tid < 128) {
+            const int r = (tid - 64) >> 3, cc = (tid - 64) & 7;
+            A[(j0 + r) * CHOL_LD + j0 + cc] = L8[r * (CHOL_NB + 1) + cc];
+        } else if (tid < 192) {
+            const int cc = tid - 128;
+            if (cc < j0 + CHOL_NB) {
+                double bcol[CHOL_NB];
+#pragma unroll
+                for (int b = 0; b < CHOL_NB; b++) bcol[b] = B[(j0 + b) * CHOL_LD + cc];
+#pragma unroll
+                for (int aa = 0; aa < CHOL_NB; aa++) {
+                    double sacc = 0.0;
+#pragma unroll
+                    for (int b = 0; b <= aa; b++) sacc = fma(Li8[aa * (CHOL_NB + 1) + b], bcol[b], sacc);
+                    B[(j0 + aa) * CHOL_LD + cc] = sacc;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- (3) rank-8 update: trailing matrix (columns > block, lower triangle) and rows of L^{-1} below the block
+        if (j0 + CHOL_NB < LP) {
+            const bool trail = c >= j0 + CHOL_NB;
+            double mine[CHOL_NB];              // l_{c, j0+a} (trailing) or (L^{-1})_{j0+a, c} (substitution)
+#pragma unroll
+            for (int aa = 0; aa < CHOL_NB; aa++)
+                mine[aa] = trail ? A[c * CHOL_LD + j0 + aa] : B[(j0 + aa) * CHOL_LD + c];
+            double* M = trail ? A : B;
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                const int t = g + 8 * m;
+                if (t >= j0 + CHOL_NB && (!trail || c <= t)) {
+                    double acc = M[t * CHOL_LD + c];
+#pragma unroll
+                    for (int aa = 0; aa < CHOL_NB; aa++) acc = fma(-A[t * CHOL_LD + j0 + aa], mine[aa], acc);
+                    M[t * CHOL_LD + c] = acc;
+                }
             }
         }
         __syncthreads();
     }
-    if (bad && tid == 0) atomicOr(flag, 1);
-    if (tid < 64 && tid >= k) {
-        dinv[tid] = 1.0;
-        ldiag[tid] = 1.0;
-    }
-    __syncthreads();
+    if (bad && lane == 0) atomicOr(flag, 1);
     // outputs (row-major 64 x 64): R[r][i] = L[i][r], Rinv[r][i] = (L^{-1})[i][r]; thread (g, c) writes rows r = g + 8m,
     // column i = c (consecutive threads -> consecutive addresses)
 #pragma unroll
     for (int m = 0; m < 8; m++) {
         const int r = g + 8 * m, i = c;
-        const double x = (r <= i) ? B[i * CHOL_LD + r] * dinv[i] : 0.0;
+        const double x = (r <= i) ? B[i * CHOL_LD + r] : 0.0;
         if (Rinv) Rinv[r * LP + i] = x;
         if (RinvT) RinvT[r * LP + i] = (T)x;
-        if (R) R[r * LP + i] = (r < i) ? A[i * CHOL_LD + r] * dinv[r] : ((r == i) ? ldiag[r] : 0.0);
+        if (R) R[r * LP + i] = (r <= i) ? A[i * CHOL_LD + r] : 0.0;
     }
 }
 
@@ -315,81 +385,167 @@ template void cast_mat64<float>(salg_ctx*, const double*, float*, const double*)
 template void cast_mat64<double>(salg_ctx*, const double*, double*, const double*);
 
 // ---- one-sided Jacobi SVD of a k x k matrix, one CTA of 32 warps ---------------------------------------------
-// A = U diag(S) V^T, S descending.  Rows of W hold the columns of A (so a column rotation touches two
+// A = U diag(S) V^T, S descending.  Rows of W hold the columns of A V (so a column rotation touches two
 // contiguous shared-memory rows); one warp per pair, round-robin tournament ordering.
-__global__ void __launch_bounds__(1024)
-jacobi_svd64_kernel(const double* __restrict__ A, int k, double* __restrict__ U, double* __restrict__ S,
-                    double* __restrict__ V, int* __restrict__ flag) {
-    extern __shared__ __align__(16) unsigned char dyn_smem[];
-    double (*W)[LP + 1] = reinterpret_cast<double (*)[LP + 1]>(dyn_smem);
-    double (*Vt)[LP + 1] = W + LP;
-    __shared__ double sig[LP];
-    __shared__ int order[LP];
-    __shared__ int s_rot;
+// The ~59 rounds x ~8 sweeps are a serial chain of latencies (shuffle reductions, reciprocal / square root, barrier),
+// and this kernel is replicated on every GPU of a row-sharded fit (0.75 ms in f64 throughout).  So the bulk of the sweeps
+// runs in f32 (half the shuffles, hardware rsqrt / rcp), the accumulated V is then re-orthonormalised in f64 by two
+// Newton-Schulz steps V <- V (3 I - V^T V) / 2 (f32 orthogonality error 1e-6 -> 1e-12 -> below f64 rounding),
+// W = A V is recomputed in f64 and f64 sweeps finish the job (typically one rotating sweep and one confirming sweep).
+template <typename F> struct JacMath;
+template <> struct JacMath<double> {
+    static __device__ __forceinline__ double rcp(double x) { return __drcp_rn(x); }
+    static __device__ __forceinline__ double rsq(double x) { return rsqrt(x); }
+};
+template <> struct JacMath<float> {
+    static __device__ __forceinline__ float rcp(float x) { return __frcp_rn(x); }
+    static __device__ __forceinline__ float rsq(float x) { return rsqrtf(x); }
+};
+
+// returns the number of rotating sweeps; *s_rot is block-shared scratch.  EIGHT lanes per pair (lane s owns elements
+// s, s + 8, ..., s + 56 of the two rows), four pairs per warp, 8 warps: the three dot products of a pair then cost three
+// shuffle levels instead of five and a quarter of the shuffle instructions — with one warp per pair the 30 warps' 900
+// shuffle instructions per round (f64: two each) ran into the SM's one-shuffle-per-clock limit (1.6 us per round).
+// Only the first JAC_WARPS warps take part (named barrier); the caller __syncthreads() afterwards.
+constexpr int JAC_WARPS = 8;
+template <typename F>
+__device__ __forceinline__ int jacobi_sweeps(F (*W)[LP + 1], F (*Vt)[LP + 1], int ke, F tol, int max_sweeps, int* s_rot) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < LP * LP; i += 1024) {
-        int r = i >> 6, c = i & 63;
-        W[c][r] = (r < k && c < k) ? A[r * LP + c] : 0.0;
-        Vt[r][c] = (r == c) ? 1.0 : 0.0;
-    }
-    __syncthreads();
-    const int ke = (k + 1) & ~1;        // even number of players (a zero column pads odd k)
+    if (warp >= JAC_WARPS) return 0;
     const int n_pairs = ke / 2;
-    const double tol = 1.5e-14;   // ~ k * eps: below the rounding noise of the k-term dot products
+    const int sub = lane & 7, pair = warp * 4 + (lane >> 3);
+    const bool active = pair < n_pairs;
+    auto bar = [] { asm volatile("bar.sync 1, %0;" ::"n"(JAC_WARPS * 32) : "memory"); };
     int sweep = 0;
-    for (; sweep < 30; sweep++) {
-        if (tid == 0) s_rot = 0;
-        __syncthreads();
+    for (; sweep < max_sweeps; sweep++) {
+        if (tid == 0) *s_rot = 0;
+        bar();
         for (int round = 0; round < ke - 1; round++) {
-            if (warp < n_pairs) {
-                int p, q;
-                if (warp == 0) {
+            int p = 0, q = 1;
+            if (active) {
+                if (pair == 0) {
                     p = round % (ke - 1);
                     q = ke - 1;
                 } else {
-                    p = (round + warp) % (ke - 1);
-                    q = (round - warp + (ke - 1)) % (ke - 1);
+                    p = (round + pair) % (ke - 1);
+                    q = (round - pair + (ke - 1)) % (ke - 1);
                 }
                 if (p > q) { int t = p; p = q; q = t; }
-                double wp0 = W[p][lane], wp1 = W[p][lane + 32];
-                double wq0 = W[q][lane], wq1 = W[q][lane + 32];
-                double alpha = wp0 * wp0 + wp1 * wp1;
-                double beta = wq0 * wq0 + wq1 * wq1;
-                double gamma = wp0 * wq0 + wp1 * wq1;
-#pragma unroll
-                for (int o = 16; o; o >>= 1) {
-                    alpha += __shfl_xor_sync(0xFFFFFFFFu, alpha, o);
-                    beta += __shfl_xor_sync(0xFFFFFFFFu, beta, o);
-                    gamma += __shfl_xor_sync(0xFFFFFFFFu, gamma, o);
-                }
-                if (fabs(gamma) > tol * sqrt(alpha * beta) && gamma != 0.0) {
-                    // rotation from fast reciprocal / reciprocal-square-root intrinsics: the 59 rounds x ~8 sweeps are a
-                    // serial chain, divisions and square roots were most of its latency
-                    double zeta = (beta - alpha) * __drcp_rn(2.0 * gamma);
-                    double h2 = fma(zeta, zeta, 1.0);
-                    double w = h2 * rsqrt(h2);                                   // sqrt(1 + zeta^2)
-                    double t = (zeta >= 0.0 ? 1.0 : -1.0) * __drcp_rn(fabs(zeta) + w);
-                    double c = rsqrt(fma(t, t, 1.0)), s = c * t;
-                    W[p][lane] = c * wp0 - s * wq0;
-                    W[p][lane + 32] = c * wp1 - s * wq1;
-                    W[q][lane] = s * wp0 + c * wq0;
-                    W[q][lane + 32] = s * wp1 + c * wq1;
-                    double vp0 = Vt[p][lane], vp1 = Vt[p][lane + 32];
-                    double vq0 = Vt[q][lane], vq1 = Vt[q][lane + 32];
-                    Vt[p][lane] = c * vp0 - s * vq0;
-                    Vt[p][lane + 32] = c * vp1 - s * vq1;
-                    Vt[q][lane] = s * vp0 + c * vq0;
-                    Vt[q][lane + 32] = s * vp1 + c * vq1;
-                    if (lane == 0) s_rot = 1;
-                }
             }
-            __syncthreads();
+            F wp[8], wq[8];
+            F alpha = F(0), beta = F(0), gamma = F(0);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                wp[i] = W[p][8 * i + sub];
+                wq[i] = W[q][8 * i + sub];
+                alpha = fma(wp[i], wp[i], alpha);
+                beta = fma(wq[i], wq[i], beta);
+                gamma = fma(wp[i], wq[i], gamma);
+            }
+#pragma unroll
+            for (int o = 4; o; o >>= 1) {
+                alpha += __shfl_xor_sync(0xFFFFFFFFu, alpha, o);
+                beta += __shfl_xor_sync(0xFFFFFFFFu, beta, o);
+                gamma += __shfl_xor_sync(0xFFFFFFFFu, gamma, o);
+            }
+            // |gamma| > tol sqrt(alpha beta)  <=>  gamma^2 > tol^2 alpha beta  (no square root on the chain)
+            if (active && gamma * gamma > tol * tol * alpha * beta && gamma != F(0)) {
+                F zeta = (beta - alpha) * JacMath<F>::rcp(F(2) * gamma);
+                F h2 = fma(zeta, zeta, F(1));
+                F w = h2 * JacMath<F>::rsq(h2);                                   // sqrt(1 + zeta^2)
+                F t = (zeta >= F(0) ? F(1) : F(-1)) * JacMath<F>::rcp(fabs(zeta) + w);
+                F c = JacMath<F>::rsq(fma(t, t, F(1))), sn = c * t;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    W[p][8 * i + sub] = c * wp[i] - sn * wq[i];
+                    W[q][8 * i + sub] = sn * wp[i] + c * wq[i];
+                    const F vp = Vt[p][8 * i + sub], vq = Vt[q][8 * i + sub];
+                    Vt[p][8 * i + sub] = c * vp - sn * vq;
+                    Vt[q][8 * i + sub] = sn * vp + c * vq;
+                }
+                if (sub == 0) *s_rot = 1;
+            }
+            bar();
         }
-        int any = s_rot;
-        __syncthreads();
+        int any = *s_rot;
+        bar();
         if (!any) break;
     }
+    return sweep;
+}
+
+// C[i][j] (64 x 64, ld 65) = sum_m X[i][m] * Y[m][j]  (transX: X[m][i];  transY: Y[j][m]); 1024 threads, 4 outputs each
+template <bool TX, bool TY>
+__device__ __forceinline__ void mat64_smem(const double (*X)[LP + 1], const double (*Y)[LP + 1], double (*Cm)[LP + 1]) {
+    const int tid = threadIdx.x;
+    const int j = tid & 63, i0 = (tid >> 6) * 4;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int m = 0; m < LP; m++) {
+        const double y = TY ? Y[j][m] : Y[m][j];
+#pragma unroll
+        for (int u = 0; u < 4; u++) acc[u] = fma(TX ? X[m][i0 + u] : X[i0 + u][m], y, acc[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) Cm[i0 + u][j] = acc[u];
+}
+
+constexpr int JAC_SMEM = (4 * LP * (LP + 1)) * 8 + (2 * LP * (LP + 1)) * 4;
+
+__global__ void __launch_bounds__(1024)
+jacobi_svd64_kernel(const double* __restrict__ A, int k, double* __restrict__ U, double* __restrict__ S,
+                    double* __restrict__ V, int* __restrict__ flag, int f32_sweeps, float tol32, int* __restrict__ dbg_sweeps) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    double (*W)[LP + 1] = reinterpret_cast<double (*)[LP + 1]>(dyn_smem);
+    double (*Vt)[LP + 1] = W + LP;
+    double (*At)[LP + 1] = Vt + LP;        // At[c][r] = A[r][c]
+    double (*T1)[LP + 1] = At + LP;        // scratch
+    float (*W32)[LP + 1] = reinterpret_cast<float (*)[LP + 1]>(T1 + LP);
+    float (*V32)[LP + 1] = W32 + LP;
+    __shared__ double sig[LP];
+    __shared__ int order[LP];
+    __shared__ int s_rot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < LP * LP; i += 1024) {
+        int r = i >> 6, c = i & 63;
+        const double a = (r < k && c < k) ? A[r * LP + c] : 0.0;
+        W[c][r] = a;
+        At[c][r] = a;
+        W32[c][r] = (float)a;
+        Vt[r][c] = (r == c) ? 1.0 : 0.0;
+        V32[r][c] = (r == c) ? 1.f : 0.f;
+    }
+    __syncthreads();
+    const int ke = (k + 1) & ~1;        // even number of players (a zero column pads odd k)
+    if (f32_sweeps > 0) {
+        // scale-free in f32: the rotations only see ratios, but keep the entries in range
+        const int s32 = jacobi_sweeps<float>(W32, V32, ke, tol32, f32_sweeps, &s_rot);
+        if (dbg_sweeps && tid == 0) dbg_sweeps[0] = s32;
+        __syncthreads();
+        // Vt <- orth(V32): two Newton-Schulz steps in f64.  Vt rows are the columns of V: (V^T V)[i][j] = <Vt[i], Vt[j]>
+        for (int i = tid; i < LP * LP; i += 1024) Vt[i >> 6][i & 63] = (double)V32[i >> 6][i & 63];
+        __syncthreads();
+        for (int it = 0; it < 2; it++) {
+            mat64_smem<false, true>(Vt, Vt, T1);                 // T1 = Vt Vt^T = V^T V
+            __syncthreads();
+            for (int i = tid; i < LP * LP; i += 1024) {
+                const int r = i >> 6, c = i & 63;
+                T1[r][c] = (r == c ? 1.5 : 0.0) - 0.5 * T1[r][c];
+            }
+            __syncthreads();
+            mat64_smem<false, false>(T1, Vt, W);                 // V <- V (1.5 I - 0.5 V^T V)  <=>  Vt <- (...)^T Vt, symmetric
+            __syncthreads();
+            for (int i = tid; i < LP * LP; i += 1024) Vt[i >> 6][i & 63] = W[i >> 6][i & 63];
+            __syncthreads();
+        }
+        // W[p][r] = sum_j A[r][j] V[j][p] = sum_j At[j][r] Vt[p][j]
+        mat64_smem<false, false>(Vt, At, W);
+        __syncthreads();
+    }
+    const double tol = 1.5e-14;   // ~ k * eps: below the rounding noise of the k-term dot products
+    const int sweep = jacobi_sweeps<double>(W, Vt, ke, tol, 30, &s_rot);
+    __syncthreads();
     if (tid == 0 && sweep >= 30) atomicOr(flag, 2);
+    if (dbg_sweeps && tid == 0) dbg_sweeps[1] = sweep;
     // singular values = row norms of W
     if (warp < 2) {
         int p = tid;   // 0..63
@@ -429,9 +585,19 @@ jacobi_svd64_kernel(const double* __restrict__ A, int k, double* __restrict__ U,
 
 void jacobi_svd64(salg_ctx* ctx, const double* d_A, int k, double* d_U, double* d_S, double* d_V, int* d_flag) {
     ProfScope ps(ctx, PROF_JACOBI, 0.0);
-    constexpr int kSmem = 2 * LP * (LP + 1) * 8;
-    set_max_dyn_smem(jacobi_svd64_kernel, (int)(kSmem));
-    jacobi_svd64_kernel<<<1, 1024, kSmem, ctx->stream>>>(d_A, k, d_U, d_S, d_V, d_flag);
+    static const int f32_sweeps = getenv("SALG_JACOBI_F32") ? atoi(getenv("SALG_JACOBI_F32")) : 10;
+    static const float tol32 = getenv("SALG_JACOBI_TOL32") ? (float)atof(getenv("SALG_JACOBI_TOL32")) : 4e-6f;
+    static const bool dbg = getenv("SALG_JACOBI_DBG") != nullptr;
+    DevBuf<int> d_dbg(dbg ? 2 : 0, ctx->stream);
+    set_max_dyn_smem(jacobi_svd64_kernel, (int)(JAC_SMEM));
+    jacobi_svd64_kernel<<<1, 1024, JAC_SMEM, ctx->stream>>>(d_A, k, d_U, d_S, d_V, d_flag, f32_sweeps, tol32,
+                                                            dbg ? d_dbg.get() : nullptr);
+    if (dbg) {
+        int h[2] = {0, 0};
+        cudaMemcpyAsync(h, d_dbg.get(), 8, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        fprintf(stderr, "[jacobi] k=%d f32 sweeps %d (tol %.1e), f64 sweeps %d\n", k, h[0], (double)tol32, h[1]);
+    }
     ctx->n_launch++;
     SALG_CUDA(cudaGetLastError());
 }

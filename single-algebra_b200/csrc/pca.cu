@@ -60,6 +60,33 @@ __global__ void panel_sub_kernel(T* __restrict__ a, const T* __restrict__ b, int
     for (; i < n; i += stride) a[i] = a[i] - b[i];
 }
 
+// Streamed fit: the matrix stays in (pinned) host memory and crosses PCIe ONCE, chunk by chunk, through the masked
+// statistics + fused compaction pass; only the kept entries (scaled scratch) and the tile format stay on the device.
+struct HostCsrSrc {
+    const int64_t* off;
+    const int32_t* idx;
+    const void* val;
+};
+struct StreamFallback {};      // thrown when a streamed fit has to be redone from a resident upload
+
+// one warp per row of a staged chunk: column indices in range and strictly increasing (what csr_upload checks)
+__global__ void validate_rows_kernel(const int64_t* __restrict__ ptr, const uint32_t* __restrict__ col, int64_t nrows,
+                                     uint32_t ncols, int* __restrict__ flag) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    int bad = 0;
+    for (int64_t r = w; r < nrows; r += nw) {
+        const int64_t s = ptr[r], e = ptr[r + 1];
+        for (int64_t p = s + lane; p < e; p += 32) {
+            const uint32_t c = col[p];
+            if (c >= ncols) bad |= 1;
+            if (p + 1 < e && c >= col[p + 1]) bad |= 4;
+        }
+    }
+    if (bad) atomicOr(flag, bad);
+}
+
 template <typename T>
 static void pca_release(salg_pca* p) {
     if (!p) return;
@@ -78,7 +105,8 @@ static void pca_destroy(salg_pca* p) {
 
 template <typename T>
 static salg_pca* pca_fit(salg_ctx* ctx, const salg_csr* x, const salg_pca_params* prm, const uint8_t* mask,
-                         int64_t mask_len, const T* omega, int64_t omega_rows, int64_t omega_cols) {
+                         int64_t mask_len, const T* omega, int64_t omega_rows, int64_t omega_cols,
+                         const HostCsrSrc* host = nullptr) {
     SALG_REQUIRE(ctx && x && prm, SALG_ERR_BAD_ARG, "ctx/x/params is NULL");
     SALG_REQUIRE(x->dtype == dtype_of<T>::value, SALG_ERR_BAD_ARG, "csr value type does not match the entry point");
     SALG_REQUIRE(prm->n_components >= 1, SALG_ERR_BAD_ARG, "n_components must be >= 1");
@@ -146,9 +174,98 @@ static salg_pca* pca_fit(salg_ctx* ctx, const salg_csr* x, const salg_pca_params
                 kept_val = (T*)(kept_col + n_slots);
                 SALG_CUDA(cudaMemsetAsync(d_ovf.get(), 0, 4, st));
             }
+            if (host) {
+                if constexpr (std::is_same<T, float>::value) {
+                    if (!fused_compact) throw StreamFallback{};
+                    // ---- streamed statistics + compaction: double-buffered row chunks, copy stream || compute stream
+                    ProfScope ps(ctx, PROF_H2D, (double)x->nnz * 8.0);
+                    cudaStream_t cs = ctx->copy_stream;
+                    SALG_CUDA(cudaMemsetAsync(d_sum.get(), 0, (size_t)ncols * 8, st));
+                    SALG_CUDA(cudaMemsetAsync(d_sq.get(), 0, (size_t)ncols * 8, st));
+                    SALG_CUDA(cudaMemsetAsync(d_row_kept.get(), 0, (size_t)(x->nrows + 1) * 8, st));
+                    DevBuf<int> d_val_flag(1, st);
+                    SALG_CUDA(cudaMemsetAsync(d_val_flag.get(), 0, 4, st));
+                    // chunks of ~nnz / 16 entries (>= 16 Mi), cut at row boundaries
+                    const int64_t target = getenv("SALG_STREAM_CHUNK") ? std::max<int64_t>(1, atoll(getenv("SALG_STREAM_CHUNK")))
+                                                                       : std::max<int64_t>(x->nnz / 16, (int64_t)1 << 24);
+                    std::vector<int64_t> cut{0};
+                    while (cut.back() < x->nrows) {
+                        const int64_t r0 = cut.back();
+                        const int64_t* lo = std::upper_bound(host->off + r0 + 1, host->off + x->nrows + 1, host->off[r0] + target);
+                        int64_t r1 = (int64_t)(lo - host->off) - 1;
+                        if (r1 <= r0) r1 = r0 + 1;
+                        if (r1 > x->nrows) r1 = x->nrows;
+                        cut.push_back(r1);
+                    }
+                    int64_t cap = 0;
+                    for (size_t k = 0; k + 1 < cut.size(); k++) cap = std::max(cap, host->off[cut[k + 1]] - host->off[cut[k]]);
+                    uint32_t* s_idx[2];
+                    float* s_val[2];
+                    cudaEvent_t copied[2], done[2];
+                    for (int b = 0; b < 2; b++) {
+                        s_idx[b] = (uint32_t*)dev_alloc(ctx, ((size_t)cap + 32) * 4);
+                        s_val[b] = (float*)dev_alloc(ctx, ((size_t)cap + 32) * 4);
+                        SALG_CUDA(cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
+                        SALG_CUDA(cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming));
+                    }
+                    cudaEvent_t ready;
+                    SALG_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+                    SALG_CUDA(cudaEventRecord(ready, st));                  // staging buffers / accumulators exist and are zeroed
+                    SALG_CUDA(cudaStreamWaitEvent(cs, ready, 0));
+                    bool intsum = !getenv("SALG_STATS_NO_INT");
+                    try {
+                        for (size_t k = 0; k + 1 < cut.size(); k++) {
+                            const int b = (int)(k & 1);
+                            const int64_t r0 = cut[k], r1 = cut[k + 1], e0 = host->off[r0], n = host->off[r1] - e0;
+                            if (k >= 2) SALG_CUDA(cudaStreamWaitEvent(cs, done[b], 0));
+                            if (n) {
+                                SALG_CUDA(cudaMemcpyAsync(s_idx[b], host->idx + e0, (size_t)n * 4, cudaMemcpyHostToDevice, cs));
+                                SALG_CUDA(cudaMemcpyAsync(s_val[b], (const float*)host->val + e0, (size_t)n * 4, cudaMemcpyHostToDevice, cs));
+                            }
+                            SALG_CUDA(cudaEventRecord(copied[b], cs));
+                            SALG_CUDA(cudaStreamWaitEvent(st, copied[b], 0));
+                            if (k == 0 && intsum) intsum = col_stats_probe_int_f32(ctx, st, s_val[b], n, d_ovf.get() + 1);
+                            const int64_t nr = r1 - r0;
+                            int64_t want = ceil_div(nr * 32, 256), capg = (int64_t)ctx->sm_count * 16;
+                            validate_rows_kernel<<<(unsigned)std::max<int64_t>(1, std::min(want, capg)), 256, 0, st>>>(
+                                x->row_ptr + r0, s_idx[b] - e0, nr, (uint32_t)ncols, d_val_flag.get());
+                            ctx->n_launch++;
+                            col_stats_masked_chunk_f32(ctx, st, x->row_ptr + r0, s_idx[b] - e0, s_val[b] - e0, nr, ncols, (int64_t)run,
+                                                       d_sum.get(), d_sq.get(), d_bits.get(), d_row_kept.get() + r0, kept_col,
+                                                       (float*)kept_val, kept_shift, d_ovf.get(), intsum);
+                            SALG_CUDA(cudaEventRecord(done[b], st));
+                        }
+                        int h_flags[2] = {0, 0}, h_valid = 0;
+                        SALG_CUDA(cudaMemcpyAsync(h_flags, d_ovf.get(), 8, cudaMemcpyDeviceToHost, st));
+                        SALG_CUDA(cudaMemcpyAsync(&h_valid, d_val_flag.get(), 4, cudaMemcpyDeviceToHost, st));
+                        SALG_CUDA(cudaStreamSynchronize(st));
+                        SALG_CUDA(cudaStreamSynchronize(cs));
+                        if (h_valid & 1) throw Error(SALG_ERR_BAD_ARG, "invalid CSR: column index out of range");
+                        if (h_valid & 4)
+                            throw Error(SALG_ERR_BAD_ARG, "invalid CSR: column indices must be strictly increasing within a row");
+                        // a row overflowing its kept-entry slot, or values that are not raw counts after all: redo from a
+                        // resident upload (the accumulated sums are not reusable)
+                        if (h_flags[0] || (intsum && h_flags[1])) throw StreamFallback{};
+                    } catch (...) {
+                        cudaStreamSynchronize(cs);
+                        cudaStreamSynchronize(st);
+                        for (int b = 0; b < 2; b++) { dev_free(ctx, s_idx[b]); dev_free(ctx, s_val[b]); cudaEventDestroy(copied[b]); cudaEventDestroy(done[b]); }
+                        cudaEventDestroy(ready);
+                        throw;
+                    }
+                    for (int b = 0; b < 2; b++) { dev_free(ctx, s_idx[b]); dev_free(ctx, s_val[b]); cudaEventDestroy(copied[b]); cudaEventDestroy(done[b]); }
+                    cudaEventDestroy(ready);
+                    if (ctx->nranks > 1) {
+                        allreduce_f64(ctx, d_sum.get(), (size_t)ncols);
+                        allreduce_f64(ctx, d_sq.get(), (size_t)ncols);
+                    }
+                } else {
+                    throw StreamFallback{};
+                }
+            } else
             col_stats_device<T>(ctx, x, d_sum.get(), d_sq.get(), nullptr, d_bits.get(), d_row_kept.get(), (int64_t)run,
                                 kept_col, kept_val, kept_shift, d_ovf.get());
-            if (fused_compact) {
+            if (fused_compact && !host) {
                 int h_ovf = 0;
                 SALG_CUDA(cudaMemcpyAsync(&h_ovf, d_ovf.get(), 4, cudaMemcpyDeviceToHost, st));
                 SALG_CUDA(cudaStreamSynchronize(st));
@@ -646,6 +763,42 @@ int salg_pca_fit_f32(salg_ctx* ctx, const salg_csr* x, const salg_pca_params* pr
     return guarded([&] {
         SALG_REQUIRE(out, SALG_ERR_BAD_ARG, "out is NULL");
         *out = pca_fit<float>(ctx, x, prm, mask, mask_len, omega, orows, ocols);
+    });
+}
+int salg_pca_fit_host_f32(salg_ctx* ctx, int64_t nrows, int64_t ncols, int64_t nnz, const int64_t* row_offsets,
+                          const int32_t* col_indices, const float* values, const salg_pca_params* prm, const uint8_t* mask,
+                          int64_t mask_len, const float* omega, int64_t orows, int64_t ocols, salg_pca** out) {
+    return guarded([&] {
+        SALG_REQUIRE(ctx && out && prm && row_offsets, SALG_ERR_BAD_ARG, "NULL argument");
+        SALG_REQUIRE(nnz == 0 || (col_indices && values), SALG_ERR_BAD_ARG, "col_indices/values is NULL");
+        if (mask)
+            SALG_REQUIRE(mask_len == ncols, SALG_ERR_MASK_LEN,
+                         "The mask vector length and the number of features (columns) have to be the same!");
+        SALG_CUDA(cudaSetDevice(ctx->device));
+        const bool can_stream = mask && prm->svd_method == SALG_SVD_RANDOM && tc_enabled(ctx) && nnz > 0 && nrows > 0 &&
+                                !getenv("SALG_NO_STREAM_FIT");
+        if (can_stream) {
+            salg_csr* shell = csr_shell_from_host_offsets(ctx, SALG_F32, nrows, ncols, nnz, row_offsets);
+            HostCsrSrc src{row_offsets, col_indices, values};
+            try {
+                *out = pca_fit<float>(ctx, shell, prm, mask, mask_len, omega, orows, ocols, &src);
+                csr_destroy(shell);
+                return;
+            } catch (const StreamFallback&) {
+                csr_destroy(shell);          // redo below from a resident upload
+            } catch (...) {
+                csr_destroy(shell);
+                throw;
+            }
+        }
+        salg_csr* c = csr_upload_i32_f32(ctx, nrows, ncols, nnz, row_offsets, col_indices, values);
+        try {
+            *out = pca_fit<float>(ctx, c, prm, mask, mask_len, omega, orows, ocols);
+        } catch (...) {
+            csr_destroy(c);
+            throw;
+        }
+        csr_destroy(c);
     });
 }
 int salg_pca_fit_f64(salg_ctx* ctx, const salg_csr* x, const salg_pca_params* prm, const uint8_t* mask,

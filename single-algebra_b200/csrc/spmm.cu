@@ -191,7 +191,9 @@ template void spmm_launch<double>(salg_ctx*, int, const int64_t*, const uint32_t
 template <typename T>
 void spmm_A(salg_ctx* ctx, const salg_csr* c, const T* X, T* out, const double* corr, bool pattern) {
     if constexpr (std::is_same<T, float>::value) {
-        if (!pattern && tc_enabled(ctx)) {
+        // (shards of 2^31 or more stored entries have no tile format: A X falls back to the chunk kernel, whose offsets
+        // are 64-bit; A^T Y needs the transposed copy or the tile format, both limited to < 2^31 entries per GPU)
+        if (!pattern && tc_enabled(ctx) && c->nnz < ((int64_t)1 << 31)) {
             tc_spmm_A(ctx, c, X, out, corr);
             return;
         }

@@ -519,6 +519,47 @@ template void col_stats_device<float>(salg_ctx*, const salg_csr*, double*, doubl
 template void col_stats_device<double>(salg_ctx*, const salg_csr*, double*, double*, double*, const uint32_t*, int64_t*, int64_t,
                                        uint32_t*, void*, int, int*);
 // can col_stats_device write the kept entries (kept_col / kept_val) for this matrix / mask?
+// ---- streamed fits: the masked statistics + fused compaction pass over ONE ROW CHUNK of a host-resident matrix ------
+// ptr = device row offsets of the chunk's first row (global offsets), col / val = the chunk's staged entries rebased so
+// that col[ptr[r]] is row r's first entry (the pointers may lie below the staging buffer; only offsets inside the chunk
+// are dereferenced).  Accumulates into d_sum / d_sumsq / row_kept / the kept-entry scratch without zeroing anything, on the
+// given stream.  probe = true: returns whether the chunk's leading values look like raw counts (integer accumulators).
+bool col_stats_probe_int_f32(salg_ctx* ctx, cudaStream_t st, const float* d_val, int64_t n, int* d_flag1) {
+    const int64_t np = n < 65536 ? n : 65536;
+    if (np <= 0) return true;
+    values_integral_probe_kernel<<<(unsigned)ceil_div(np, 256), 256, 0, st>>>(d_val, np, d_flag1);
+    ctx->n_launch++;
+    int h = 0;
+    SALG_CUDA(cudaMemcpyAsync(&h, d_flag1, 4, cudaMemcpyDeviceToHost, st));
+    SALG_CUDA(cudaStreamSynchronize(st));
+    if (h) SALG_CUDA(cudaMemsetAsync(d_flag1, 0, 4, st));
+    return h == 0;
+}
+
+void col_stats_masked_chunk_f32(salg_ctx* ctx, cudaStream_t st, const int64_t* ptr, const uint32_t* col, const float* val,
+                                int64_t nrows, int64_t ncols, int64_t n_kept, double* d_sum, double* d_sumsq,
+                                const uint32_t* keepbits, int64_t* row_kept, uint32_t* kept_col, float* kept_val, int kept_shift,
+                                int* flags, bool intsum) {
+    if (nrows <= 0) return;
+    const size_t kb_bytes = (size_t)((ncols + 31) / 32) * 4;
+    const size_t need_masked = ((size_t)ncols + 2 + 2 * (size_t)n_kept) * 4 + 2 * kb_bytes + 8;
+    const int grid = (int)(nrows < ctx->sm_count ? nrows : ctx->sm_count);
+    SALG_REQUIRE(!intsum || ceil_div(nrows, grid) <= 65536, SALG_ERR_UNSUPPORTED, "row chunk too long for integer accumulators");
+    if (intsum) {
+        auto k = col_stats_masked_kernel<float, true>;
+        set_max_dyn_smem(k, 200 * 1024);
+        k<<<grid, 1024, need_masked, st>>>(ptr, col, val, nrows, (int)ncols, (int)n_kept, d_sum, d_sumsq, keepbits,
+                                           (unsigned long long*)row_kept, kept_col, kept_val, kept_shift, flags);
+    } else {
+        auto k = col_stats_masked_kernel<float, false>;
+        set_max_dyn_smem(k, 200 * 1024);
+        k<<<grid, 1024, need_masked, st>>>(ptr, col, val, nrows, (int)ncols, (int)n_kept, d_sum, d_sumsq, keepbits,
+                                           (unsigned long long*)row_kept, kept_col, kept_val, kept_shift, flags);
+    }
+    ctx->n_launch++;
+    SALG_CUDA(cudaGetLastError());
+}
+
 bool col_stats_can_fuse_compaction(const salg_csr* c, int64_t n_kept) {
     const size_t kb = (size_t)((c->ncols + 31) / 32) * 4;
     return c->dtype == SALG_F32 && ((size_t)c->ncols + 2 + 2 * (size_t)n_kept) * 4 + 2 * kb + 8 <= 200 * 1024 && !getenv("SALG_STATS_TILED");

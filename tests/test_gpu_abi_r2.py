@@ -80,7 +80,7 @@ def test_sketch_wider_than_operator_is_clamped(salg, ctx, dt, masked):
     """n_eff < n_components + n_oversamples (builder defaults 50 + 10): the sketch is clamped to the operator's dimensions
     instead of running CholeskyQR on a rank-deficient panel; the result is then the exact truncated SVD."""
     ncols = 90 if masked else 55                                   # unmasked: 55 columns < 50 + 10
-    A = planted_counts(800, ncols, seed=13, dtype=dt)
+    A = planted_counts(800, ncols, density=0.5, seed=13, dtype=dt)   # dense enough that no column is empty (full rank)
     mask = np.zeros(ncols, bool); mask[:40] = True
     n_eff = 40 if masked else ncols
     k = 35 if masked else 50
@@ -95,3 +95,68 @@ def test_sketch_wider_than_operator_is_clamped(salg, ctx, dt, masked):
     s = np.linalg.svd(Ak, compute_uv=False)[:k]
     tol = 1e-9 if dt == np.float64 else 2e-4
     assert O.rel_err(pca.singular_values_[:k - 5], s[:k - 5]) < tol
+
+
+def _host_csr(salg, ctx, A):
+    return salg.CsrMatrix(A.shape[0], A.shape[1], A.indptr.astype(np.int64).view(np.uint64), A.indices.astype(np.int32),
+                          A.data.astype(np.float32), ctx)
+
+
+@pytest.mark.parametrize("chunk", [None, 4000, 300])
+def test_streamed_host_fit_matches_resident_fit(salg, ctx, chunk, monkeypatch):
+    """salg_pca_fit_host_f32: the matrix streams through the statistics + compaction pass in row chunks (SURVEY §8f-3);
+    the model must equal the fit of the resident upload (same kernels, same order of the integer sums)."""
+    A = planted_counts(3000, 700, seed=21, dtype=np.float32)
+    A[17] = 0; A[18] = 0                                       # empty rows inside a chunk
+    A.eliminate_zeros()
+    mask = np.zeros(700, bool); mask[::4] = True
+    om = np.random.default_rng(2).standard_normal((175, 30)).astype(np.float32)
+    def build():
+        return salg.MaskedSparsePCABuilder().mask(mask.tolist()).n_components(20).svd_method(
+            salg.SVDMethod.Random(10, 5, salg.PowerIterationNormalizer.QR)).build()
+    ref = build()
+    dev = _host_csr(salg, ctx, A).to_device()
+    sc_ref = ref.fit_transform(dev, omega=om)
+    if chunk:
+        monkeypatch.setenv("SALG_STREAM_CHUNK", str(chunk))
+    p = build()
+    sc = p.fit_transform(_host_csr(salg, ctx, A), omega=om)      # host matrix -> streamed
+    assert np.array_equal(p.mean_, ref.mean_) and p.total_var_ == ref.total_var_      # integer sums: exact
+    assert O.rel_err(p.singular_values_, ref.singular_values_) < 1e-5
+    assert O.largest_principal_angle(p.components_, ref.components_) < 1e-3
+    assert np.abs(sc - sc_ref).max() < 2e-3 * np.abs(sc_ref).max()
+    oracle = O.sparse_pca_fit(sp.csr_matrix(A, dtype=np.float64), 20, omega=om.astype(np.float64), mask=mask, n_oversamples=10,
+                              n_power_iterations=5)
+    assert O.rel_err(p.singular_values_, oracle.singular_values) < 1e-4
+
+
+def test_streamed_host_fit_falls_back_on_non_count_values(salg, ctx, monkeypatch):
+    """Values that stop being raw counts after the probed prefix (or never were) still give the right model: f32
+    accumulators from the start, or a redo from a resident upload."""
+    A = planted_counts(2500, 400, seed=23, dtype=np.float32)
+    A.data[A.nnz // 2:] += 0.25                                # integers first, fractions in later chunks
+    mask = np.zeros(400, bool); mask[1::3] = True
+    om = np.random.default_rng(3).standard_normal((int(mask.sum()), 24)).astype(np.float32)
+    monkeypatch.setenv("SALG_STREAM_CHUNK", "20000")
+    p = salg.MaskedSparsePCABuilder().mask(mask.tolist()).n_components(16).svd_method(
+        salg.SVDMethod.Random(8, 5, salg.PowerIterationNormalizer.QR)).build()
+    p.fit(_host_csr(salg, ctx, A), omega=om)
+    oracle = O.sparse_pca_fit(sp.csr_matrix(A, dtype=np.float64), 16, omega=om.astype(np.float64), mask=mask, n_oversamples=8,
+                              n_power_iterations=5)
+    assert O.rel_err(p.singular_values_, oracle.singular_values) < 1e-4
+    assert np.allclose(p.mean_, oracle.mean, rtol=1e-5, atol=1e-7)
+
+
+def test_streamed_host_fit_rejects_malformed_rows(salg, ctx):
+    A = planted_counts(600, 200, seed=25, dtype=np.float32)
+    mask = np.ones(200, bool)
+    x = _host_csr(salg, ctx, A)
+    bad = x.col_indices.copy()
+    s0, s1 = int(A.indptr[5]), int(A.indptr[6])
+    assert s1 - s0 >= 2
+    bad[s0], bad[s0 + 1] = bad[s0 + 1], bad[s0]                  # not strictly increasing inside row 5
+    x.col_indices = bad
+    p = salg.MaskedSparsePCABuilder().mask(mask.tolist()).n_components(5).svd_method(
+        salg.SVDMethod.Random(5, 2, salg.PowerIterationNormalizer.QR)).build()
+    with pytest.raises(salg.SalgError, match="strictly increasing"):
+        p.fit(x)

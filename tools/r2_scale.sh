@@ -1,0 +1,22 @@
+#!/bin/bash
+# usage: r2_scale.sh N  — multi-GPU run of round 2: 2-rank NCCL parity test (N = 2), cfg3 (strong scaling, with the parity
+# of the N-rank fit against a single-GPU fit in the JSON line) and cfg5 (weak scaling: 500k rows per GPU) through torchrun.
+N=$1
+O=gpurun_out/r2n$N
+mkdir -p $O
+if [ "$N" = "2" ]; then
+timeout 900 python -m pytest tests/test_gpu_dist.py -m gpu -q --timeout 900 -s > $O/t_dist.log 2>&1; echo "dist exit $?"; tail -3 $O/t_dist.log
+fi
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 10 --warmup 3 > $O/bench_cfg3.log 2> $O/bench_cfg3.err; echo "bench cfg3 n$N exit $?"; tail -2 $O/bench_cfg3.err
+timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 5 --warmup 3 --workload cfg5 > $O/bench_cfg5.log 2> $O/bench_cfg5.err; echo "bench cfg5 n$N exit $?"; tail -2 $O/bench_cfg5.err
+python - <<PY
+import json
+for w in ("cfg3", "cfg5"):
+    try:
+        d=json.loads([l for l in open('$O/bench_%s.log' % w) if l.startswith('{')][-1])
+    except Exception as e:
+        print(w, "no line", e); continue
+    print(w, 'n', d['n_gpus'], 'ms_per_step', round(d['ms_per_step'],2), 'value', round(d['value']), 'e2e', d['e2e'] and d['e2e'].get('ms_per_step') and round(d['e2e']['ms_per_step'],1), 'parity', d.get('parity_vs_n1'))
+    n=d['steps']
+    print({k:(round(v['ms_total']/n,2), v['launches']//n, v.get('frac_of_hbm_peak') and round(v['frac_of_hbm_peak'],3)) for k,v in d['kernel_classes'].items()})
+PY
