@@ -493,6 +493,7 @@ def _cpu_baseline(s, spec, wl, mask, om, host, pca_dev, make_pca, ctx):
         if wl.get("cpu_rows") and wl["cpu_rows"] < rows_cfg:        # bounded sample for the big shard
             rows = wl["cpu_rows"]
             ptr = off[:rows + 1]
+            cidx, cval = cidx[:int(ptr[rows])], cval[:int(ptr[rows])]
     else:
         rows = min(rows_cfg, 40_000)
         ptr, cidx, cval = R.synth_rows(spec, 0, rows)

@@ -46,8 +46,12 @@ def main():
             p = b.n_components(30).svd_method(s.SVDMethod.Random(10, 7, s.PowerIterationNormalizer.QR)).build()
             sc = p.fit_transform(x, omega=om)
             ref = O.sparse_pca_fit(A.astype(np.float64), 30, omega=om.astype(np.float64), mask=mask)
-            assert O.rel_err(p.singular_values_, ref.singular_values) < stol, (dtype, mask is None)
-            assert O.largest_principal_angle(p.components_, ref.components) < 1e-3
+            serr, ang = O.rel_err(p.singular_values_, ref.singular_values), O.largest_principal_angle(p.components_, ref.components)
+            if rank == 0:
+                print(f"[dist check] world {world} {np.dtype(dtype).name} {'unmasked' if mask is None else 'masked'} randomized fit: "
+                      f"sigma rel err {serr:.2e} (< {stol:.0e}), largest principal angle {ang:.2e} rad (< 1e-3)", flush=True)
+            assert serr < stol, (dtype, mask is None)
+            assert ang < 1e-3
             assert np.allclose(p.mean_, ref.mean, rtol=1e-4, atol=1e-12)
             ex = O.transform(A, p.components_, p.mean_, mask=mask, mode=O.EXACT)[r0:r1]
             assert np.abs(sc - ex).max() < (1e-9 if dtype == np.float64 else 3e-4) * np.abs(ex).max()
@@ -55,6 +59,9 @@ def main():
         p = s.SparsePCABuilder().n_components(15).build()
         p.fit(x)
         u, sv, vt = O.truncated_svd_truth(A.astype(np.float64), 15)
+        if rank == 0:
+            print(f"[dist check] world {world} {np.dtype(dtype).name} Lanczos: sigma rel err {O.rel_err(p.singular_values_, sv):.2e}, "
+                  f"angle {O.largest_principal_angle(p.components_, vt):.2e} rad", flush=True)
         assert O.rel_err(p.singular_values_, sv) < stol
         assert O.largest_principal_angle(p.components_, vt) < 1e-3
     dist.barrier()
