@@ -62,8 +62,9 @@ class Context:
         return ms.value
 
     def set_spmm_impl(self, impl: str):
-        """'tc' (tcgen05 tile-densified, default for f32) or 'chunk' (CUDA-core kernels)."""
-        N.check(N.load().salg_ctx_set_spmm_impl(self._h, {'tc': 0, 'chunk': 1}[impl]))
+        """'tm' (tcgen05, sparse operand expanded into TMEM: default for f32), 'tc' (tcgen05, dense tile in shared memory)
+        or 'chunk' (CUDA-core kernels)."""
+        N.check(N.load().salg_ctx_set_spmm_impl(self._h, {'tc': 0, 'chunk': 1, 'tm': 2}[impl]))
 
     def launch_count(self) -> int:
         n = C.c_int64()

@@ -177,7 +177,9 @@ static salg_ctx* ctx_new(int device) {
     c->sm_count = prop.multiProcessorCount;
     {
         const char* e = getenv("SALG_SPMM_IMPL");
-        c->spmm_impl = (e && strcmp(e, "chunk") == 0) ? 1 : 0;
+        // default: tcgen05 products with the sparse operand expanded into TMEM (tm.cu); "tc" = the dense-tile generation
+        // (tc.cu, also the fallback for operators wider than the TMEM-operand builder supports), "chunk" = CUDA cores
+        c->spmm_impl = (e && strcmp(e, "chunk") == 0) ? 1 : (e && strcmp(e, "tc") == 0) ? 0 : 2;
     }
     SALG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     SALG_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
@@ -344,7 +346,8 @@ int salg_timer_stop(salg_ctx* c, double* ms) {
 int salg_ctx_set_spmm_impl(salg_ctx* c, int impl) {
     return guarded([&] {
         SALG_REQUIRE(c, SALG_ERR_BAD_ARG, "ctx is NULL");
-        SALG_REQUIRE(impl == 0 || impl == 1, SALG_ERR_BAD_ARG, "impl must be 0 (tcgen05) or 1 (chunk)");
+        SALG_REQUIRE(impl >= 0 && impl <= 2, SALG_ERR_BAD_ARG,
+                     "impl must be 0 (tcgen05, dense tile in shared memory), 1 (chunk) or 2 (tcgen05, sparse operand in TMEM)");
         c->spmm_impl = impl;
     });
 }

@@ -28,6 +28,7 @@
 #include <cuda_fp16.h>
 
 #include "common.cuh"
+#include "tcgen05.cuh"
 
 namespace salg {
 
@@ -97,11 +98,6 @@ constexpr int TC_ATY_TMEM_COLS = 512 / TC_ATY_OCC;
 constexpr int TC_NSB = TC_NSB_;       // sparse operand buffers (A X): pass P (unit * terms + term) uses buffer P % NSB
 constexpr int TC_ATY_NSB = TC_ATY_NSB_;   // the same for A^T Y (its dense stages are twice as large)
 constexpr int TC_EPT = (TC_SLOT_ENTRIES + TC_GROUP_THREADS - 1) / TC_GROUP_THREADS;   // ring entries per thread and tile
-constexpr uint32_t TC_SPIN_LIMIT = 1u << 24;
-// suspend-time hint of mbarrier.try_wait: a waiting thread sleeps in hardware until the phase completes (or this many
-// ns pass) instead of re-issuing the poll; with the default hint the ~25 waiting lanes of a CTA were measured to take
-// most of the issue slots of the SM (ncu: 62 % issue utilisation, three quarters of it poll loops)
-constexpr uint32_t TC_WAIT_HINT_NS = 200000u;
 
 struct TcTiles {
     uint2* entries = nullptr;       // [nnz] .x = half byte-offsets in the A X (bits 0-13) and A^T Y (bits 14-27) operand
@@ -111,153 +107,31 @@ struct TcTiles {
     int a_terms = 2;                // 1 when every value is exact in fp16
     float a_scale = 1.f;            // power of two applied to the operator values before the split
     int64_t nnz = 0;
+    void* tm = nullptr;             // TMEM-operand format (tm.cu) instead of entries / tile_ptr
 };
+
+// tm.cu
+void tm_free(salg_ctx* owner, void* tiles);
+bool tm_supported(const salg_csr* c);
+void* tm_build(salg_ctx* ctx, const salg_csr* c, const int64_t* in_ptr, const uint32_t* in_col, const float* in_val, int in_shift);
+int tm_n_rb(const void* tiles);
+int tm_terms(const void* tiles);
+float tm_scale(const void* tiles);
+void tm_spmm_A(salg_ctx* ctx, const salg_csr* c, void* tiles, const float* X, float* Y, const double* corr, unsigned* d_amax);
+void tm_aty_launch(salg_ctx* ctx, const salg_csr* c, void* tiles, const uint8_t* Yprep, const float* scales, float* Z);
+static bool tm_wanted(const salg_ctx* ctx, const salg_csr* c) { return ctx->spmm_impl == 2 && tm_supported(c); }
 
 void tc_free(salg_ctx* owner, void* p) {
     TcTiles* t = (TcTiles*)p;
     if (!t) return;
+    tm_free(owner, t->tm);
     dev_free(owner, t->entries);
     dev_free(owner, t->tile_ptr);
     delete t;
 }
 
-// ---- PTX helpers ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
 __device__ unsigned long long g_tc_dbg[32];   // timing experiment counters of CTA 0 (SALG_TC_DBG=32)
 #define TC_T(acc) do { long long _t = clock64(); acc += _t - t_prev; t_prev = _t; } while (0)
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t addr = smem_u32(bar), ok = 0, spins = 0;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(addr), "r"(parity), "r"(TC_WAIT_HINT_NS)
-            : "memory");
-        if (!ok && ++spins > TC_SPIN_LIMIT) __trap();   // never hang the GPU on a protocol bug
-    } while (!ok);
-}
-// the same wait without the suspend hint, for the two hand-offs that sit on the critical chain of a unit (scatter group
-// <- MMAs retired, MMA issuer <- operand built): waking from a long suspend was measured against polling
-#ifndef TC_FAST_WAITS_
-#define TC_FAST_WAITS_ 0
-#endif
-__device__ __forceinline__ void mbar_wait_crit(uint64_t* bar, uint32_t parity) {
-    if (!TC_FAST_WAITS_) { mbar_wait(bar, parity); return; }
-    uint32_t addr = smem_u32(bar), ok = 0, spins = 0;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(addr), "r"(parity)
-            : "memory");
-        if (!ok && ++spins > TC_SPIN_LIMIT) __trap();
-    } while (!ok);
-}
-// one lane polls, the warp follows
-__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane) {
-    if (lane == 0) mbar_wait(bar, parity);
-    __syncwarp();
-}
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(smem_dst)),
-                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// Four consecutive K-steps (K = 16 fp16 each) of one product in ONE asm block: the issuing thread is the serial
-// resource of the CTA, so per-MMA overhead is two 64-bit adds.  Descriptor start addresses advance by a_step /
-// b_step (16 B units) per K-step; only the first MMA may overwrite the accumulator.
-__device__ __forceinline__ void umma_f16_run4(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                              uint32_t accumulate_first, uint64_t a_step, uint64_t b_step) {
-    asm volatile(
-        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "setp.eq.b32 q, 0, 0;\n\t"
-        "mov.b64 da, %1;\n\tmov.b64 db, %2;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
-        "add.u64 da, da, %5;\n\tadd.u64 db, db, %6;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, q;\n\t"
-        "add.u64 da, da, %5;\n\tadd.u64 db, db, %6;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, q;\n\t"
-        "add.u64 da, da, %5;\n\tadd.u64 db, db, %6;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, q;\n\t"
-        "}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate_first), "l"(a_step), "l"(b_step)
-        : "memory");
-}
-// shared-memory matrix descriptor, K-major, no swizzle: core matrix = 8 rows x 16 B (128 B contiguous);
-// LBO = byte distance between the two 16 B K-chunks of one instruction, SBO = distance between 8-row groups
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
-}
-// instruction descriptor: D f32 (bit 4), A/B fp16 (format 0), both K-major, M = 128, N as given
-__host__ __device__ constexpr uint32_t tc_idesc(uint32_t n) { return (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24); }
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// fp16 term `t` (0, 1) of a scaled float: x ~ h0 + h1 with 11 significant bits each
-__device__ __forceinline__ unsigned short f16_term(float x, int t) {
-    __half h = __float2half_rn(x);
-    if (t > 0) h = __float2half_rn(x - __half2float(h));
-    return __half_as_ushort(h);
-}
-
-// byte offset of element (mn, k) inside a canonical K-major no-swizzle operand whose 16 B K-chunks are
-// `chunk_stride` bytes apart (8-row groups are 128 B apart)
-__device__ __forceinline__ uint32_t canon_off(uint32_t mn, uint32_t k, uint32_t chunk_stride) {
-    return (k >> 3) * chunk_stride + (mn >> 3) * 128u + (mn & 7u) * 16u + (k & 7u) * 2u;
-}
-
-// power-of-two scale that puts `amax` just below 2^14 (fp16 max is 65504; the second term is 2^-11 smaller)
-__host__ __device__ inline float tc_pow2_scale(float amax) {
-    if (!(amax > 0.f) || !isfinite(amax)) return 1.f;
-    int e;
-    frexpf(amax, &e);                 // amax = f * 2^e, f in [0.5, 1)
-    return ldexpf(1.f, 14 - e);
-}
 
 // ---- tile format builder -----------------------------------------------------------------------------------------
 template <typename T>
@@ -529,6 +403,21 @@ void* tc_build(salg_ctx* ctx, const salg_csr* c, const int64_t* in_ptr = nullptr
         in_ptr = c->row_ptr;
         in_col = c->col;
         in_val = (const T*)c->val;
+    }
+    if (tm_wanted(ctx, c)) {
+        TcTiles* t = new TcTiles();
+        try {
+            t->tm = tm_build(ctx, c, in_ptr, in_col, (const float*)in_val, in_shift);
+        } catch (...) {
+            delete t;
+            throw;
+        }
+        t->n_rb = tm_n_rb(t->tm);
+        t->n_cb = (int)ceil_div(c->ncols, TC_CB);
+        t->nnz = c->nnz;
+        t->a_terms = tm_terms(t->tm);
+        t->a_scale = tm_scale(t->tm);
+        return t;
     }
     SALG_REQUIRE(c->nnz < ((int64_t)1 << 31), SALG_ERR_UNSUPPORTED, "tile format supports < 2^31 stored entries per GPU shard");
     TcTiles* t = new TcTiles();
@@ -1420,7 +1309,7 @@ __global__ void tc_init_z_kernel(float* __restrict__ Z, int64_t n_eff, const flo
     Z[i] = (mu && cs) ? (float)(-(double)mu[i >> 6] * cs[i & 63]) : 0.f;
 }
 
-bool tc_enabled(const salg_ctx* ctx) { return ctx->spmm_impl == 0; }
+bool tc_enabled(const salg_ctx* ctx) { return ctx->spmm_impl != 1; }
 
 // L2 prefetch distance of the entry lists, in units (SALG_TC_PFD overrides; 0 = off)
 static int tc_pfd() {
@@ -1430,8 +1319,29 @@ static int tc_pfd() {
 }
 
 static TcTiles* tiles_of(salg_ctx* ctx, const salg_csr* c) {
+    if (c->tc && (((TcTiles*)c->tc)->tm != nullptr) != tm_wanted(ctx, c)) {   // the context switched product generations
+        SALG_CUDA(cudaStreamSynchronize(ctx->stream));
+        tc_free(ctx, c->tc);
+        c->tc = nullptr;
+    }
     if (!c->tc) c->tc = tc_build<float>(ctx, c);
     return (TcTiles*)c->tc;
+}
+
+// d_scales = {s, 1 / (s a_scale)} with s the power of two that puts max |P| just below 2^14 (tm.cu uses it too)
+void tc_panel_scales(salg_ctx* ctx, const float* P, int64_t n, float a_scale, float* d_scales, unsigned* d_amax) {
+    cudaStream_t st = ctx->stream;
+    SALG_CUDA(cudaMemsetAsync(d_amax, 0, 4, st));
+    if (n > 0) {
+        int64_t ne = n * LP;
+        int64_t want = ceil_div(ne, 256 * 8);
+        int64_t cap = (int64_t)ctx->sm_count * 8;
+        tc_absmax_kernel<<<(unsigned)(want < cap ? (want > 0 ? want : 1) : cap), 256, 0, st>>>(P, ne, d_amax);
+        ctx->n_launch++;
+    }
+    tc_scale_kernel<<<1, 1, 0, st>>>(d_amax, a_scale, d_scales);
+    ctx->n_launch++;
+    SALG_CUDA(cudaGetLastError());
 }
 
 // scale + split the panel into the canonical dense operand (device-side scale: no host round trip)
@@ -1475,6 +1385,10 @@ void tc_spmm_A(salg_ctx* ctx, const salg_csr* c, const float* X, float* Y, const
     if (c->nrows == 0) return;
     double bytes = (double)c->nnz * 8 + (double)(c->nrows + 1) * 8 + (double)c->ncols * 60 * 4 + (double)c->nrows * 60 * 4;
     ProfScope ps(ctx, PROF_SPMM, bytes);   // includes the panel pre-split
+    if (t->tm) {
+        tm_spmm_A(ctx, c, t->tm, X, Y, corr, d_amax);
+        return;
+    }
     DevBuf<uint8_t> Xprep((size_t)t->n_cb * AxSmem::D_BYTES, st);
     DevBuf<float> scales(2, st);
     DevBuf<unsigned> amax(1, st);
@@ -1596,6 +1510,10 @@ void tc_spmm_At(salg_ctx* ctx, const salg_csr* c, const float* Y, float* Z, cons
 
 static void tc_aty_launch(salg_ctx* ctx, const salg_csr* c, TcTiles* t, const uint8_t* Yprep, const float* scales, float* Z) {
     cudaStream_t st = ctx->stream;
+    if (t->tm) {
+        tm_aty_launch(ctx, c, t->tm, Yprep, scales, Z);
+        return;
+    }
     int n_groups = (int)ceil_div(t->n_cb, AtySmem::G);
     int n_rb_real = (int)ceil_div(c->nrows, TC_RB);
     int ranges = ctx->sm_count * TC_ATY_OCC / n_groups;

@@ -92,7 +92,7 @@ def test_tc_products_match_chunk_kernels_and_f64(salg, ctx):
             got_tc = salg.op_spmm(d, X, mu=mu, transposed=transposed)
             ctx.set_spmm_impl("chunk")
             got_ch = salg.op_spmm(d, X, mu=mu, transposed=transposed)
-            ctx.set_spmm_impl("tc")
+            ctx.set_spmm_impl("tm")        # the context's default
             scale = np.abs(ref).max()
             assert np.abs(got_tc - ref).max() <= 2e-5 * scale, (make_general, transposed)
             assert np.abs(got_ch - ref).max() <= 2e-5 * scale
@@ -118,6 +118,7 @@ def test_tc_products_dense_tiles_and_tiny_shapes(salg, ctx):
             # scale of the un-centred product (a one-row matrix is annihilated by the centring)
             scale = np.abs(_ref_products(A, X, None, transposed)).max()
             assert np.abs(got - ref).max() <= 2e-5 * scale, (shape, dens, transposed)
+    ctx.set_spmm_impl("tm")                # the context's default
 
 
 @pytest.mark.gpu

@@ -1,0 +1,6 @@
+#!/bin/bash
+O=gpurun_out/r2b3
+mkdir -p $O
+timeout 900 python -m pytest tests/test_gpu_tm.py -m gpu -q -x --timeout 300 2>&1 | tail -8
+SALG_SPMM_IMPL=tm SALG_TM_DBG=1 SALG_LIB_PATH=scratch/libsalg_dbg.so timeout 300 python tools/scripts_tc_probe2.py 2>&1 | grep -E "^\[tm|adjoint" | tail -28 | awk "NR<=4 || NR>24"
+SALG_SPMM_IMPL=tm timeout 300 python tools/scripts_tc_probe2.py 2>&1 | tail -2
