@@ -47,7 +47,7 @@ constexpr int TM_THREADS = (TM_BUILD_WARPS + 9) * 32;   // + 4 epilogue, 2 MMA i
 #define TM_NA_ 4
 #endif
 #ifndef TM_NS_
-#define TM_NS_ 13
+#define TM_NS_ 8
 #endif
 #ifndef TM_NB_
 #define TM_NB_ 3
@@ -62,12 +62,19 @@ constexpr int TM_SLOT_BYTES = TM_REC + TM_SLOT_QUADS * 8;
 constexpr int TM_NB = TM_NB_;            // panel stages
 constexpr int TM_STAGE_BYTES = 32768;    // one panel block: 128 (N) x 128 (K) fp16
 constexpr int TM_A_COL0 = 256;           // TMEM columns [0, 256): accumulators, [256, 512): sparse-operand buffers
-constexpr int TM_SMEM = TM_NB * TM_STAGE_BYTES + TM_NS * TM_SLOT_BYTES + 128;
+constexpr int TM_EPI_PITCH = 144;         // A X epilogue staging: 32 rows x 128 B per warp, rows 144 B apart (conflict-free both ways)
+constexpr int TM_EPI_BYTES = 4 * 32 * TM_EPI_PITCH;
+constexpr int TM_SMEM = TM_NB * TM_STAGE_BYTES + TM_NS * TM_SLOT_BYTES + TM_EPI_BYTES + 128;
 constexpr int TM_PF = 8;                 // L2 prefetch distance of the tile records, in passes of one loader
 constexpr int TM_GC = 2;                 // A^T Y: operator column blocks (accumulators of 128 TMEM columns) per work item
 constexpr int TM_MAX_CB = 288;           // builder keeps masks + offsets of one row block in shared memory (772 B per tile)
 static_assert(TM_NA * 64 <= 256, "sparse-operand buffers exceed their TMEM half");
 static_assert((TM_NA & (TM_NA - 1)) == 0, "A-buffer ring is a power of two (index = pass & (n - 1))");
+// Parity waits are only safe on a barrier with ONE waiting role that sees every phase in order (a waiter a phase early would
+// alias with the phase before).  Pass p is expanded by set p % 4 into A buffer p % 4 from ring slot p % TM_NS, loaded by
+// loader p % 2: with TM_NS a multiple of 4 every slot has one loader and one expander set, every A buffer one set; the issuer
+// of A buffer x is x % 2 resp. (x / terms) % 2 within a group, and the issuers re-synchronise between groups (acc_free).
+static_assert(TM_NS % 4 == 0 && TM_NA == TM_SETS, "slot -> (loader, expander set) and A buffer -> set must be fixed");
 static_assert(TM_SMEM <= 227 * 1024, "shared memory");
 
 struct TmFormat {
@@ -622,6 +629,7 @@ tm_product_kernel(const TmArgs g) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint8_t* sStage = smem_raw;
     uint8_t* sRing = sStage + TM_NB * TM_STAGE_BYTES;
+    uint8_t* sEpi = sRing + TM_NS * TM_SLOT_BYTES;
     __shared__ uint64_t e_full[TM_NS], e_free[TM_NS], a_full[TM_NA], a_free[TM_NA], d_full[TM_NB], d_free[TM_NB], acc_full[2], acc_free[2];
     __shared__ uint32_t s_tmem;
     __shared__ float s_corr[LP];
@@ -928,21 +936,32 @@ tm_product_kernel(const TmArgs g) {
                     const uint32_t t0 = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)((grp & 1u) * 2u + h) * 64u;
 #pragma unroll 1
                     for (int c = 0; c < 2; c++) {
+                        // lane = row: 32 accumulator columns -> staging (row pitch 144 B), then the warp stores four rows x
+                        // 128 contiguous bytes per instruction (a lane writing its own row touched 32 lines per instruction:
+                        // measured 13 % of the kernel)
                         uint32_t v[32];
                         tmem_ld32(t0 + c * 32, v);
-                        if (rowi < g.n_out) {
-                            float4* dst = reinterpret_cast<float4*>(g.out + rowi * LP + c * 32);
+                        uint8_t* stg = sEpi + (size_t)qd * (32 * TM_EPI_PITCH);
 #pragma unroll
-                            for (int j = 0; j < 8; j++) {
-                                float4 y;
-                                y.x = __uint_as_float(v[4 * j]) * inv - s_corr[c * 32 + 4 * j];
-                                y.y = __uint_as_float(v[4 * j + 1]) * inv - s_corr[c * 32 + 4 * j + 1];
-                                y.z = __uint_as_float(v[4 * j + 2]) * inv - s_corr[c * 32 + 4 * j + 2];
-                                y.w = __uint_as_float(v[4 * j + 3]) * inv - s_corr[c * 32 + 4 * j + 3];
-                                amax = fmaxf(amax, fmaxf(fmaxf(fabsf(y.x), fabsf(y.y)), fmaxf(fabsf(y.z), fabsf(y.w))));
-                                dst[j] = y;
-                            }
+                        for (int j = 0; j < 8; j++) {
+                            float4 y;
+                            y.x = __uint_as_float(v[4 * j]) * inv - s_corr[c * 32 + 4 * j];
+                            y.y = __uint_as_float(v[4 * j + 1]) * inv - s_corr[c * 32 + 4 * j + 1];
+                            y.z = __uint_as_float(v[4 * j + 2]) * inv - s_corr[c * 32 + 4 * j + 2];
+                            y.w = __uint_as_float(v[4 * j + 3]) * inv - s_corr[c * 32 + 4 * j + 3];
+                            if (rowi < g.n_out) amax = fmaxf(amax, fmaxf(fmaxf(fabsf(y.x), fabsf(y.y)), fmaxf(fabsf(y.z), fabsf(y.w))));
+                            *reinterpret_cast<float4*>(stg + lane * TM_EPI_PITCH + j * 16) = y;
                         }
+                        __syncwarp();
+                        const int64_t row_w = rowi - lane;                       // first row of this warp
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const int rr = i * 4 + (lane >> 3);
+                            const float4 y = *reinterpret_cast<const float4*>(stg + rr * TM_EPI_PITCH + (lane & 7) * 16);
+                            if (row_w + rr < g.n_out && !(g.dbg & 64))
+                                *reinterpret_cast<float4*>(g.out + (row_w + rr) * LP + c * 32 + (lane & 7) * 4) = y;
+                        }
+                        __syncwarp();
                     }
                 }
             } else {
