@@ -137,46 +137,59 @@ __host__ __device__ inline int64_t tm_region(int64_t first_entry, int64_t rb, in
     return (first_entry + rb * (int64_t)n_cb * (TM_REC_Q + 2) + 1) & ~(int64_t)1;
 }
 
-constexpr int TM_BUILD_THREADS = 512;
 // One CTA per 128-row block and orientation.  Sweep 1 ORs the quad masks in shared memory; the lanes' quad counts are
-// prefix-summed per tile (offsets) and over the block's tiles (tile starts); sweep 2 (the block's entries are L2 resident
+// prefix-summed per tile (offsets) and over the block's tiles (record starts); sweep 2 (the block's entries are L2 resident
 // by then) writes every value as one fp16 into its quad.  TRANS: lanes = columns, k = rows (operand of A^T Y).
-template <bool TRANS>
-__global__ void __launch_bounds__(TM_BUILD_THREADS)
+// A warp walks a row in batches of 4 x 32 entries with every load issued before the first use (one load per trip left the
+// sweeps latency bound: 61 ms per orientation for a 500k x 33k shard); wide operators, whose masks leave room for one CTA
+// per SM only, run 1024 threads.
+template <bool TRANS, int THREADS>
+__global__ void __launch_bounds__(THREADS)
 tm_build_kernel(const int64_t* __restrict__ in_ptr, int in_shift, const int64_t* __restrict__ ptr, const uint32_t* __restrict__ col,
                 const float* __restrict__ val, int64_t nrows, int n_rb_real, int n_cb, int terms, float a_scale,
                 uint64_t* __restrict__ info, uint2* __restrict__ q_hi, uint2* __restrict__ q_lo) {
     extern __shared__ uint32_t tm_bsm[];
     uint32_t* s_mask = tm_bsm;                                      // [n_cb][128]
-    uint32_t* s_start = s_mask + (size_t)n_cb * TM_LANES;           // [n_cb] tile totals, then tile starts
+    uint32_t* s_start = s_mask + (size_t)n_cb * TM_LANES;           // [n_cb] tile totals, then record starts
     unsigned short* s_off = reinterpret_cast<unsigned short*>(s_start + n_cb);   // [n_cb][128]
-    __shared__ uint32_t s_wsum[TM_BUILD_THREADS / 32];
+    __shared__ uint32_t s_wsum[THREADS / 32];
     __shared__ uint32_t s_total;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = TM_BUILD_THREADS / 32;
+    constexpr int NW = THREADS / 32;
+    constexpr int BU = 4;
     for (int rb = blockIdx.x; rb < n_rb_real; rb += gridDim.x) {
         const int64_t r0 = (int64_t)rb * TM_LANES;
         const int64_t r1 = r0 + TM_LANES < nrows ? r0 + TM_LANES : nrows;
         const int64_t qbase = tm_region(ptr[r0], rb, n_cb);
         __syncthreads();
-        for (int i = tid; i < n_cb * TM_LANES; i += TM_BUILD_THREADS) s_mask[i] = 0;
+        for (int i = tid; i < n_cb * TM_LANES; i += THREADS) s_mask[i] = 0;
         __syncthreads();
         // sweep 1: quad masks
         for (int64_t r = r0 + warp; r < r1; r += NW) {
             const int64_t s = in_ptr[r] >> in_shift;
             const int len = (int)(ptr[r + 1] - ptr[r]);
             const unsigned lr = (unsigned)(r - r0);
-            for (int p = lane; p < len; p += 32) {
-                const unsigned c = col[s + p];
-                const unsigned j = c >> 7;
-                const unsigned li = TRANS ? (c & 127u) : lr;
-                const unsigned q = TRANS ? (lr >> 2) : ((c & 127u) >> 2);
-                atomicOr(&s_mask[j * TM_LANES + li], 1u << q);
+            const uint32_t* __restrict__ cr = col + s;
+            for (int p0 = 0; p0 < len; p0 += 32 * BU) {
+                unsigned c[BU];
+#pragma unroll
+                for (int u = 0; u < BU; u++) {
+                    const int q = p0 + lane + 32 * u;
+                    c[u] = q < len ? cr[q] : 0xFFFFFFFFu;
+                }
+#pragma unroll
+                for (int u = 0; u < BU; u++) {
+                    if (c[u] == 0xFFFFFFFFu) continue;
+                    const unsigned j = c[u] >> 7;
+                    const unsigned li = TRANS ? (c[u] & 127u) : lr;
+                    const unsigned q = TRANS ? (lr >> 2) : ((c[u] & 127u) >> 2);
+                    atomicOr(&s_mask[j * TM_LANES + li], 1u << q);
+                }
             }
         }
         __syncthreads();
-        // lanes' quad offsets inside every tile (four tiles per trip) and the tiles' quad counts
-        for (int j0 = 0; j0 < n_cb; j0 += TM_BUILD_THREADS / TM_LANES) {
+        // lanes' quad offsets inside every tile (THREADS / 128 tiles per trip) and the tiles' quad counts
+        for (int j0 = 0; j0 < n_cb; j0 += THREADS / TM_LANES) {
             const int j = j0 + (tid >> 7), li = tid & 127;
             const unsigned cnt = j < n_cb ? (unsigned)__popc(s_mask[j * TM_LANES + li]) : 0u;
             unsigned incl = cnt;
@@ -195,7 +208,7 @@ tm_build_kernel(const int64_t* __restrict__ in_ptr, int in_shift, const int64_t*
             }
             __syncthreads();
         }
-        // tile starts (even) inside the block's region
+        // record starts (even) inside the block's region
         if (warp == 0) {
             unsigned run = 0;
             for (int j0 = 0; j0 < n_cb; j0 += 32) {
@@ -219,15 +232,16 @@ tm_build_kernel(const int64_t* __restrict__ in_ptr, int in_shift, const int64_t*
         }
         __syncthreads();
         const unsigned total = s_total;
-        for (unsigned i = tid; i < total; i += TM_BUILD_THREADS) {
-            q_hi[qbase + i] = make_uint2(0u, 0u);
-            if (terms > 1) q_lo[qbase + i] = make_uint2(0u, 0u);
+        // zero the block's region (16 B stores: the region starts at an even quad and `total` is even)
+        for (int t = 0; t < terms; t++) {
+            uint4* z = reinterpret_cast<uint4*>((t ? q_lo : q_hi) + qbase);
+            for (unsigned i = tid; i < total / 2; i += THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
         }
         __syncthreads();
         // record prefixes: {first payload quad, count} + masks + offsets, in both term streams
         for (int t = 0; t < terms; t++) {
             uint2* qs = t ? q_lo : q_hi;
-            for (int i = tid; i < n_cb * TM_LANES; i += TM_BUILD_THREADS) {
+            for (int i = tid; i < n_cb * TM_LANES; i += THREADS) {
                 const int j = i >> 7, li = i & 127;
                 uint8_t* rec = reinterpret_cast<uint8_t*>(qs + qbase + s_start[j]);
                 reinterpret_cast<uint32_t*>(rec + 16)[li] = s_mask[i];
@@ -246,18 +260,30 @@ tm_build_kernel(const int64_t* __restrict__ in_ptr, int in_shift, const int64_t*
             const int64_t s = in_ptr[r] >> in_shift;
             const int len = (int)(ptr[r + 1] - ptr[r]);
             const unsigned lr = (unsigned)(r - r0);
-            for (int p = lane; p < len; p += 32) {
-                const unsigned c = col[s + p];
-                const float x = val[s + p] * a_scale;
-                const unsigned j = c >> 7;
-                const unsigned li = TRANS ? (c & 127u) : lr;
-                const unsigned k = TRANS ? lr : (c & 127u);
-                const unsigned q = k >> 2, e = k & 3u;
-                const unsigned m = s_mask[j * TM_LANES + li];
-                const int64_t pos = qbase + s_start[j] + TM_REC_Q + s_off[j * TM_LANES + li] + __popc(m & ((1u << q) - 1u));
-                const __half hh = __float2half_rn(x);
-                h_hi[pos * 4 + e] = __half_as_ushort(hh);
-                if (terms > 1) h_lo[pos * 4 + e] = __half_as_ushort(__float2half_rn(x - __half2float(hh)));
+            const uint32_t* __restrict__ cr = col + s;
+            const float* __restrict__ vr = val + s;
+            for (int p0 = 0; p0 < len; p0 += 32 * BU) {
+                unsigned c[BU];
+                float x[BU];
+#pragma unroll
+                for (int u = 0; u < BU; u++) {
+                    const int q = p0 + lane + 32 * u;
+                    c[u] = q < len ? cr[q] : 0xFFFFFFFFu;
+                    x[u] = q < len ? vr[q] * a_scale : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < BU; u++) {
+                    if (c[u] == 0xFFFFFFFFu) continue;
+                    const unsigned j = c[u] >> 7;
+                    const unsigned li = TRANS ? (c[u] & 127u) : lr;
+                    const unsigned k = TRANS ? lr : (c[u] & 127u);
+                    const unsigned q = k >> 2, e = k & 3u;
+                    const unsigned m = s_mask[j * TM_LANES + li];
+                    const int64_t pos = qbase + s_start[j] + TM_REC_Q + s_off[j * TM_LANES + li] + __popc(m & ((1u << q) - 1u));
+                    const __half hh = __float2half_rn(x[u]);
+                    h_hi[pos * 4 + e] = __half_as_ushort(hh);
+                    if (terms > 1) h_lo[pos * 4 + e] = __half_as_ushort(__float2half_rn(x[u] - __half2float(hh)));
+                }
             }
         }
     }
@@ -317,18 +343,20 @@ void* tm_build(salg_ctx* ctx, const salg_csr* c, const int64_t* in_ptr, const ui
                 ctx->n_launch++;
             }
             if (n_rb_real == 0) continue;
-            const int per_sm = smem > 100 * 1024 ? 1 : smem > 48 * 1024 ? 2 : 3;
+            const bool wide = smem > 100 * 1024;                 // one CTA per SM: 1024 threads
+            const int per_sm = wide ? 1 : smem > 48 * 1024 ? 2 : 3;
             const int grid = std::min(n_rb_real, ctx->sm_count * per_sm);
+            auto launch = [&](auto kernel, int threads) {
+                set_max_dyn_smem(kernel, (int)smem);
+                kernel<<<grid, threads, smem, st>>>(in_ptr, in_shift, c->row_ptr, in_col, in_val, c->nrows, n_rb_real, t->n_cb, t->a_terms,
+                                                    t->a_scale, f.info, f.q_hi, f.q_lo);
+            };
             if (o == 0) {
-                set_max_dyn_smem(tm_build_kernel<false>, (int)smem);
-                tm_build_kernel<false><<<grid, TM_BUILD_THREADS, smem, st>>>(in_ptr, in_shift, c->row_ptr, in_col, in_val, c->nrows,
-                                                                            n_rb_real, t->n_cb, t->a_terms, t->a_scale, f.info,
-                                                                            f.q_hi, f.q_lo);
+                if (wide) launch(tm_build_kernel<false, 1024>, 1024);
+                else launch(tm_build_kernel<false, 512>, 512);
             } else {
-                set_max_dyn_smem(tm_build_kernel<true>, (int)smem);
-                tm_build_kernel<true><<<grid, TM_BUILD_THREADS, smem, st>>>(in_ptr, in_shift, c->row_ptr, in_col, in_val, c->nrows,
-                                                                           n_rb_real, t->n_cb, t->a_terms, t->a_scale, f.info,
-                                                                           f.q_hi, f.q_lo);
+                if (wide) launch(tm_build_kernel<true, 1024>, 1024);
+                else launch(tm_build_kernel<true, 512>, 512);
             }
             ctx->n_launch++;
             SALG_CUDA(cudaGetLastError());
