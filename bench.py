@@ -369,14 +369,15 @@ def run_ours(args, wl):
                for k, v in merged.items()}
     # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the two product kernels from ONE
     # `ncu --set full` capture each, on this workload at 1 GPU (profiles/, see TRAFFIC_SRC)
-    TRAFFIC_SRC = "profiles/r01_v3_ncu_full_tc_ax_aty.csv"
-    ncu_traffic = {("cfg3", "spmm"): 1.122587e9 + 0.238028e9, ("cfg3", "spmm_t"): 1.468230e9 + 0.004183e9}
+    TRAFFIC_SRC = "profiles/r02_ncu_full_tm_products.csv"
+    ncu_traffic = {("cfg3", "spmm"): 1.094948e9 + 0.235534e9, ("cfg3", "spmm_t"): 1.236483e9 + 0.006493e9}
     dom = max((k for k in ("spmm", "spmm_t") if k in prof), key=lambda k: prof[k][0], default=None)
     roofline = None
     if dom:
         tms, n, b = prof[dom]
         achieved = b / tms / 1e6     # GB/s
-        roofline = {"bound": "hbm", "kernel": ("tc_aty_kernel (A^T Y, tcgen05 tile-densified)" if dom == "spmm_t" else "tc_ax_kernel (A X, tcgen05 tile-densified)"),
+        roofline = {"bound": "hbm", "kernel": ("tm_product_kernel<true> (A^T Y, tcgen05.mma with the sparse operand expanded into TMEM)" if dom == "spmm_t"
+                               else "tm_product_kernel<false> (A X, tcgen05.mma with the sparse operand expanded into TMEM)"),
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": ncu_traffic.get((args.workload, dom)) if world == 1 else None,
                     "traffic_source": TRAFFIC_SRC if world == 1 and (args.workload, dom) in ncu_traffic else None,

@@ -137,6 +137,7 @@ void set_max_dyn_smem_impl(const void* kernel, int bytes) {
 void allreduce_f64(salg_ctx* ctx, double* buf, size_t n) {
     if (ctx->nranks <= 1 || n == 0) return;
     ProfScope ps(ctx, PROF_ALLREDUCE, (double)n * 8);
+    if (p2p_allreduce(ctx, buf, n, nullptr, 0)) return;
     SALG_NCCL(ncclAllReduce(buf, buf, n, ncclDouble, ncclSum, ctx->comm, ctx->stream));
 }
 
@@ -144,6 +145,7 @@ void allreduce_f64(salg_ctx* ctx, double* buf, size_t n) {
 void allreduce_gram_and_panel(salg_ctx* ctx, double* gram, size_t n_gram, float* panel, size_t n_panel) {
     if (ctx->nranks <= 1) return;
     ProfScope ps(ctx, PROF_ALLREDUCE, (double)n_gram * 8 + (double)n_panel * 4);
+    if (p2p_allreduce(ctx, gram, n_gram, panel, n_panel)) return;
     SALG_NCCL(ncclGroupStart());
     if (n_gram) SALG_NCCL(ncclAllReduce(gram, gram, n_gram, ncclDouble, ncclSum, ctx->comm, ctx->stream));
     if (n_panel) SALG_NCCL(ncclAllReduce(panel, panel, n_panel, ncclFloat, ncclSum, ctx->comm, ctx->stream));
@@ -154,6 +156,7 @@ template <>
 void allreduce_T<float>(salg_ctx* ctx, float* buf, size_t n) {
     if (ctx->nranks <= 1 || n == 0) return;
     ProfScope ps(ctx, PROF_ALLREDUCE, (double)n * 4);
+    if (p2p_allreduce(ctx, nullptr, 0, buf, n)) return;
     SALG_NCCL(ncclAllReduce(buf, buf, n, ncclFloat, ncclSum, ctx->comm, ctx->stream));
 }
 template <>
@@ -253,6 +256,12 @@ int salg_ctx_create_dist(int device, int rank, int nranks, const void* uid, salg
                 salg_ctx_destroy(c);
                 throw Error(SALG_ERR_NCCL, m);
             }
+            try {
+                p2p_init(c);            // collective; leaves NCCL as the only path if any rank cannot map its peers
+            } catch (...) {
+                salg_ctx_destroy(c);
+                throw;
+            }
         }
         *out = c;
     });
@@ -277,6 +286,7 @@ int salg_ctx_destroy(salg_ctx* c) {
             if (i == 0 && c->stream) small_cache_release(c->stream);
             if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
         }
+        p2p_destroy(c);
         if (c->comm) ncclCommDestroy(c->comm);
         if (c->stream) cudaStreamDestroy(c->stream);
         if (c->copy_stream) cudaStreamDestroy(c->copy_stream);

@@ -127,6 +127,7 @@ struct salg_ctx {
     // allocation of that size on every fit, which was measured to cost more than the kernels using it)
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
+    void* p2p = nullptr;           // peer-memory all-reduce state (p2p.cu), nullptr = NCCL only
 };
 
 struct salg_csr {
@@ -331,6 +332,11 @@ template <typename T> void panel_pack(salg_ctx* ctx, const T* src, int64_t m, in
 template <typename T> void panel_unpack(salg_ctx* ctx, const T* src, int64_t m, int k, T* dst);    // (m x 64) -> (m x k)
 template <typename T> void cholqr2(salg_ctx* ctx, T* Y, int64_t m_local, int k, bool sharded, double* d_colsum64,
                                    double* d_Rtot, int* d_flag, int passes);
+
+// p2p.cu: one-shot all-reduce over NVLink peer memory (small operands); collective init right after the NCCL communicator
+void p2p_init(salg_ctx* ctx);
+void p2p_destroy(salg_ctx* ctx);
+bool p2p_allreduce(salg_ctx* ctx, double* buf64, size_t n64, float* buf32, size_t n32);
 
 void allreduce_f64(salg_ctx* ctx, double* buf, size_t n);
 void allreduce_gram_and_panel(salg_ctx* ctx, double* gram, size_t n_gram, float* panel, size_t n_panel);

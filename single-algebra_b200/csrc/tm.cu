@@ -67,7 +67,7 @@ constexpr int TM_EPI_BYTES = 4 * 32 * TM_EPI_PITCH;
 constexpr int TM_SMEM = TM_NB * TM_STAGE_BYTES + TM_NS * TM_SLOT_BYTES + TM_EPI_BYTES + 128;
 constexpr int TM_PF = 8;                 // L2 prefetch distance of the tile records, in passes of one loader
 constexpr int TM_GC = 2;                 // A^T Y: operator column blocks (accumulators of 128 TMEM columns) per work item
-constexpr int TM_MAX_CB = 288;           // builder keeps masks + offsets of one row block in shared memory (772 B per tile)
+constexpr int TM_MAX_CB = 1 << 20;       // (the builder works chunk by chunk: no width limit of its own)
 static_assert(TM_NA * 64 <= 256, "sparse-operand buffers exceed their TMEM half");
 static_assert((TM_NA & (TM_NA - 1)) == 0, "A-buffer ring is a power of two (index = pass & (n - 1))");
 // Parity waits are only safe on a barrier with ONE waiting role that sees every phase in order (a waiter a phase early would
@@ -137,23 +137,32 @@ __host__ __device__ inline int64_t tm_region(int64_t first_entry, int64_t rb, in
     return (first_entry + rb * (int64_t)n_cb * (TM_REC_Q + 2) + 1) & ~(int64_t)1;
 }
 
-// One CTA per 128-row block and orientation.  Sweep 1 ORs the quad masks in shared memory; the lanes' quad counts are
-// prefix-summed per tile (offsets) and over the block's tiles (record starts); sweep 2 (the block's entries are L2 resident
-// by then) writes every value as one fp16 into its quad.  TRANS: lanes = columns, k = rows (operand of A^T Y).
-// A warp walks a row in batches of 4 x 32 entries with every load issued before the first use (one load per trip left the
-// sweeps latency bound: 61 ms per orientation for a 500k x 33k shard); wide operators, whose masks leave room for one CTA
-// per SM only, run 1024 threads.
-template <bool TRANS, int THREADS>
-__global__ void __launch_bounds__(THREADS)
+// One CTA per 128-row block and orientation; the block's tiles are built CHUNK by chunk (`ch` consecutive tiles):
+//   sweep 1  every warp walks its rows from a per-row cursor to the chunk's last column and ORs the quad masks (shared memory)
+//   offsets  the lanes' quad counts are prefix-summed per tile, the tiles' record starts continue the block's running total
+//   sweep 2  the same entries again (L2 resident): every value lands as one fp16 in an IMAGE of the chunk's records in shared
+//            memory, which is then written out with coalesced 16-byte stores
+// Scattering the 2-byte stores straight to global memory measured ~55 partial-sector writes per clock on the whole chip —
+// 1.2-1.5 ms per orientation at config 3, 26 ms for a 500k x 33k shard — and made the masks of ALL tiles of a row block live
+// in shared memory (a 38k-column limit).  A chunk whose records do not fit the image is scattered directly (dense data).
+// TRANS: lanes = columns, k = rows (operand of A^T Y).  A warp walks a row in batches of 4 x 32 entries, loads first.
+constexpr int TM_BUILD_THREADS = 512;
+template <bool TRANS>
+__global__ void __launch_bounds__(TM_BUILD_THREADS)
 tm_build_kernel(const int64_t* __restrict__ in_ptr, int in_shift, const int64_t* __restrict__ ptr, const uint32_t* __restrict__ col,
                 const float* __restrict__ val, int64_t nrows, int n_rb_real, int n_cb, int terms, float a_scale,
-                uint64_t* __restrict__ info, uint2* __restrict__ q_hi, uint2* __restrict__ q_lo) {
-    extern __shared__ uint32_t tm_bsm[];
-    uint32_t* s_mask = tm_bsm;                                      // [n_cb][128]
-    uint32_t* s_start = s_mask + (size_t)n_cb * TM_LANES;           // [n_cb] tile totals, then record starts
-    unsigned short* s_off = reinterpret_cast<unsigned short*>(s_start + n_cb);   // [n_cb][128]
+                uint64_t* __restrict__ info, uint2* __restrict__ q_hi, uint2* __restrict__ q_lo, int ch, unsigned img_quads) {
+    constexpr int THREADS = TM_BUILD_THREADS;
+    extern __shared__ __align__(16) uint32_t tm_bsm[];
+    uint32_t* s_mask = tm_bsm;                                      // [ch][128]
+    uint32_t* s_start = s_mask + (size_t)ch * TM_LANES;             // [ch] tile totals, then record starts (from the region's start)
+    unsigned short* s_off = reinterpret_cast<unsigned short*>(s_start + ch);     // [ch][128]
+    uint2* s_img = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(tm_bsm) + (((size_t)ch * (TM_LANES * 4 + 4 + TM_LANES * 2) + 15) & ~(size_t)15));
     __shared__ uint32_t s_wsum[THREADS / 32];
     __shared__ uint32_t s_total;
+    __shared__ int s_cur0[TM_LANES], s_cur1[TM_LANES];              // per row: first entry of the chunk, first entry after it
+    __shared__ long long s_row[TM_LANES];                           // per row: first stored entry
+    __shared__ int s_len[TM_LANES];                                 // ... and their number
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = THREADS / 32;
     constexpr int BU = 4;
@@ -161,130 +170,156 @@ tm_build_kernel(const int64_t* __restrict__ in_ptr, int in_shift, const int64_t*
         const int64_t r0 = (int64_t)rb * TM_LANES;
         const int64_t r1 = r0 + TM_LANES < nrows ? r0 + TM_LANES : nrows;
         const int64_t qbase = tm_region(ptr[r0], rb, n_cb);
+        unsigned run = 0;                                           // quads of the block's region used so far (even)
         __syncthreads();
-        for (int i = tid; i < n_cb * TM_LANES; i += THREADS) s_mask[i] = 0;
-        __syncthreads();
-        // sweep 1: quad masks
-        for (int64_t r = r0 + warp; r < r1; r += NW) {
-            const int64_t s = in_ptr[r] >> in_shift;
-            const int len = (int)(ptr[r + 1] - ptr[r]);
-            const unsigned lr = (unsigned)(r - r0);
-            const uint32_t* __restrict__ cr = col + s;
-            for (int p0 = 0; p0 < len; p0 += 32 * BU) {
-                unsigned c[BU];
-#pragma unroll
-                for (int u = 0; u < BU; u++) {
-                    const int q = p0 + lane + 32 * u;
-                    c[u] = q < len ? cr[q] : 0xFFFFFFFFu;
-                }
-#pragma unroll
-                for (int u = 0; u < BU; u++) {
-                    if (c[u] == 0xFFFFFFFFu) continue;
-                    const unsigned j = c[u] >> 7;
-                    const unsigned li = TRANS ? (c[u] & 127u) : lr;
-                    const unsigned q = TRANS ? (lr >> 2) : ((c[u] & 127u) >> 2);
-                    atomicOr(&s_mask[j * TM_LANES + li], 1u << q);
-                }
-            }
+        if (tid < TM_LANES) {
+            s_cur0[tid] = 0;
+            const int64_t r = r0 + tid;
+            s_row[tid] = r < r1 ? (long long)(in_ptr[r] >> in_shift) : 0;
+            s_len[tid] = r < r1 ? (int)(ptr[r + 1] - ptr[r]) : 0;
         }
-        __syncthreads();
-        // lanes' quad offsets inside every tile (THREADS / 128 tiles per trip) and the tiles' quad counts
-        for (int j0 = 0; j0 < n_cb; j0 += THREADS / TM_LANES) {
-            const int j = j0 + (tid >> 7), li = tid & 127;
-            const unsigned cnt = j < n_cb ? (unsigned)__popc(s_mask[j * TM_LANES + li]) : 0u;
-            unsigned incl = cnt;
+        for (int jc = 0; jc < n_cb; jc += ch) {
+            const int nt = jc + ch < n_cb ? ch : n_cb - jc;
+            const unsigned c_end = (unsigned)(jc + nt) * TM_DEPTH;
+            for (int i = tid; i < nt * TM_LANES; i += THREADS) s_mask[i] = 0;
+            __syncthreads();
+            // sweep 1: quad masks of the chunk; finds every row's first entry beyond the chunk
+            for (int64_t r = r0 + warp; r < r1; r += NW) {
+                const unsigned lr = (unsigned)(r - r0);
+                const int len = s_len[lr];
+                const uint32_t* __restrict__ cr = col + s_row[lr];
+                int p0 = s_cur0[lr];
+                bool more = true;
+                while (more && p0 < len) {
+                    unsigned c[BU];
+                    const int nbt = (len - p0 + 31) >> 5;                    // sub-batches with entries (warp-uniform)
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                if (lane >= o) incl += v;
+                    for (int u = 0; u < BU; u++) {
+                        const int q = p0 + lane + 32 * u;
+                        c[u] = (u < nbt && q < len) ? cr[q] : 0xFFFFFFFFu;
+                    }
+                    int done = 0;
+#pragma unroll
+                    for (int u = 0; u < BU; u++) {
+                        if (u >= nbt) break;
+                        const bool in_chunk = c[u] < c_end;                  // (absent entries compare false)
+                        done += __popc(__ballot_sync(0xFFFFFFFFu, in_chunk));
+                        if (!in_chunk) continue;
+                        const unsigned j = (c[u] >> 7) - (unsigned)jc;
+                        const unsigned li = TRANS ? (c[u] & 127u) : lr;
+                        const unsigned q = TRANS ? (lr >> 2) : ((c[u] & 127u) >> 2);
+                        atomicOr(&s_mask[j * TM_LANES + li], 1u << q);
+                    }
+                    p0 += done;
+                    more = done == 32 * BU;                                  // a shorter batch met the chunk's (or the row's) end
+                }
+                if (lane == 0) s_cur1[lr] = p0;
             }
-            if (lane == 31) s_wsum[warp] = incl;
             __syncthreads();
-            unsigned base = 0;
-            for (int w = warp & ~3; w < warp; w++) base += s_wsum[w];
-            if (j < n_cb) {
-                s_off[j * TM_LANES + li] = (unsigned short)(base + incl - cnt);
-                if (li == TM_LANES - 1) s_start[j] = base + incl;
-            }
-            __syncthreads();
-        }
-        // record starts (even) inside the block's region
-        if (warp == 0) {
-            unsigned run = 0;
-            for (int j0 = 0; j0 < n_cb; j0 += 32) {
-                const int j = j0 + lane;
-                const unsigned tot = j < n_cb ? s_start[j] : 0u;
-                const unsigned padded = j < n_cb ? TM_REC_Q + ((tot + 1u) & ~1u) : 0u;
-                unsigned incl = padded;
+            // lanes' quad offsets inside every tile (four tiles per trip) and the tiles' quad counts
+            for (int j0 = 0; j0 < nt; j0 += THREADS / TM_LANES) {
+                const int j = j0 + (tid >> 7), li = tid & 127;
+                const unsigned cnt = j < nt ? (unsigned)__popc(s_mask[j * TM_LANES + li]) : 0u;
+                unsigned incl = cnt;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
                     const unsigned v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
                     if (lane >= o) incl += v;
                 }
-                const unsigned start = run + incl - padded;
-                if (j < n_cb) {
-                    s_start[j] = start;
-                    info[(int64_t)rb * n_cb + j] = (uint64_t)(qbase + start) | ((uint64_t)tot << 40);
+                if (lane == 31) s_wsum[warp] = incl;
+                __syncthreads();
+                unsigned base = 0;
+                for (int w = warp & ~3; w < warp; w++) base += s_wsum[w];
+                if (j < nt) {
+                    s_off[j * TM_LANES + li] = (unsigned short)(base + incl - cnt);
+                    if (li == TM_LANES - 1) s_start[j] = base + incl;
                 }
-                run += __shfl_sync(0xFFFFFFFFu, incl, 31);
+                __syncthreads();
             }
-            if (lane == 0) s_total = run;
-        }
-        __syncthreads();
-        const unsigned total = s_total;
-        // zero the block's region (16 B stores: the region starts at an even quad and `total` is even)
-        for (int t = 0; t < terms; t++) {
-            uint4* z = reinterpret_cast<uint4*>((t ? q_lo : q_hi) + qbase);
-            for (unsigned i = tid; i < total / 2; i += THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
-        }
-        __syncthreads();
-        // record prefixes: {first payload quad, count} + masks + offsets, in both term streams
-        for (int t = 0; t < terms; t++) {
-            uint2* qs = t ? q_lo : q_hi;
-            for (int i = tid; i < n_cb * TM_LANES; i += THREADS) {
-                const int j = i >> 7, li = i & 127;
-                uint8_t* rec = reinterpret_cast<uint8_t*>(qs + qbase + s_start[j]);
-                reinterpret_cast<uint32_t*>(rec + 16)[li] = s_mask[i];
-                reinterpret_cast<unsigned short*>(rec + 16 + 512)[li] = s_off[i];
-                if (li == TM_LANES - 1) {
-                    const unsigned tot = (unsigned)s_off[i] + (unsigned)__popc(s_mask[i]);
-                    *reinterpret_cast<unsigned long long*>(rec) = (unsigned long long)(qbase + s_start[j] + TM_REC_Q);
-                    *reinterpret_cast<uint2*>(rec + 8) = make_uint2(tot, 0u);
-                }
-            }
-        }
-        // sweep 2: values
-        unsigned short* h_hi = reinterpret_cast<unsigned short*>(q_hi);
-        unsigned short* h_lo = reinterpret_cast<unsigned short*>(q_lo);
-        for (int64_t r = r0 + warp; r < r1; r += NW) {
-            const int64_t s = in_ptr[r] >> in_shift;
-            const int len = (int)(ptr[r + 1] - ptr[r]);
-            const unsigned lr = (unsigned)(r - r0);
-            const uint32_t* __restrict__ cr = col + s;
-            const float* __restrict__ vr = val + s;
-            for (int p0 = 0; p0 < len; p0 += 32 * BU) {
-                unsigned c[BU];
-                float x[BU];
+            // record starts (even), continuing the block's region
+            if (warp == 0) {
+                unsigned r_run = run;
+                for (int j0 = 0; j0 < nt; j0 += 32) {
+                    const int j = j0 + lane;
+                    const unsigned tot = j < nt ? s_start[j] : 0u;
+                    const unsigned padded = j < nt ? TM_REC_Q + ((tot + 1u) & ~1u) : 0u;
+                    unsigned incl = padded;
 #pragma unroll
-                for (int u = 0; u < BU; u++) {
-                    const int q = p0 + lane + 32 * u;
-                    c[u] = q < len ? cr[q] : 0xFFFFFFFFu;
-                    x[u] = q < len ? vr[q] * a_scale : 0.f;
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const unsigned v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                        if (lane >= o) incl += v;
+                    }
+                    const unsigned start = r_run + incl - padded;
+                    if (j < nt) {
+                        s_start[j] = start;
+                        info[(int64_t)rb * n_cb + jc + j] = (uint64_t)(qbase + start) | ((uint64_t)tot << 40);
+                    }
+                    r_run += __shfl_sync(0xFFFFFFFFu, incl, 31);
                 }
-#pragma unroll
-                for (int u = 0; u < BU; u++) {
-                    if (c[u] == 0xFFFFFFFFu) continue;
-                    const unsigned j = c[u] >> 7;
-                    const unsigned li = TRANS ? (c[u] & 127u) : lr;
-                    const unsigned k = TRANS ? lr : (c[u] & 127u);
-                    const unsigned q = k >> 2, e = k & 3u;
-                    const unsigned m = s_mask[j * TM_LANES + li];
-                    const int64_t pos = qbase + s_start[j] + TM_REC_Q + s_off[j * TM_LANES + li] + __popc(m & ((1u << q) - 1u));
-                    const __half hh = __float2half_rn(x[u]);
-                    h_hi[pos * 4 + e] = __half_as_ushort(hh);
-                    if (terms > 1) h_lo[pos * 4 + e] = __half_as_ushort(__float2half_rn(x[u] - __half2float(hh)));
-                }
+                if (lane == 0) s_total = r_run;
             }
+            __syncthreads();
+            const unsigned c_quads = s_total - run;                  // the chunk's records, quads (even)
+            const bool staged = c_quads <= img_quads;                // CTA-uniform
+            for (int t = 0; t < terms; t++) {
+                uint2* qs = (t ? q_lo : q_hi) + qbase + run;         // the chunk's records in this term's stream
+                uint2* img = staged ? s_img : qs;
+                for (unsigned i = tid; i < c_quads / 2; i += THREADS) reinterpret_cast<uint4*>(img)[i] = make_uint4(0u, 0u, 0u, 0u);
+                __syncthreads();
+                // record prefixes: {first payload quad, count} + masks + offsets
+                for (int i = tid; i < nt * TM_LANES; i += THREADS) {
+                    const int j = i >> 7, li = i & 127;
+                    uint8_t* rec = reinterpret_cast<uint8_t*>(img + (s_start[j] - run));
+                    reinterpret_cast<uint32_t*>(rec + 16)[li] = s_mask[i];
+                    reinterpret_cast<unsigned short*>(rec + 16 + 512)[li] = s_off[i];
+                    if (li == TM_LANES - 1) {
+                        const unsigned tot = (unsigned)s_off[i] + (unsigned)__popc(s_mask[i]);
+                        *reinterpret_cast<unsigned long long*>(rec) = (unsigned long long)(qbase + s_start[j] + TM_REC_Q);
+                        *reinterpret_cast<uint2*>(rec + 8) = make_uint2(tot, 0u);
+                    }
+                }
+                // sweep 2: the chunk's values
+                unsigned short* h_img = reinterpret_cast<unsigned short*>(img);
+                for (int64_t r = r0 + warp; r < r1; r += NW) {
+                    const unsigned lr = (unsigned)(r - r0);
+                    const long long s = s_row[lr];
+                    const uint32_t* __restrict__ cr = col + s;
+                    const float* __restrict__ vr = val + s;
+                    const int e1 = s_cur1[lr];
+                    for (int p0 = s_cur0[lr]; p0 < e1; p0 += 32 * BU) {
+                        unsigned c[BU];
+                        float x[BU];
+                        const int nbt = (e1 - p0 + 31) >> 5;                 // sub-batches with entries (warp-uniform)
+#pragma unroll
+                        for (int u = 0; u < BU; u++) {
+                            const int q = p0 + lane + 32 * u;
+                            c[u] = (u < nbt && q < e1) ? cr[q] : 0xFFFFFFFFu;
+                            x[u] = (u < nbt && q < e1) ? vr[q] * a_scale : 0.f;
+                        }
+#pragma unroll
+                        for (int u = 0; u < BU; u++) {
+                            if (u >= nbt) break;
+                            if (c[u] == 0xFFFFFFFFu) continue;
+                            const unsigned j = (c[u] >> 7) - (unsigned)jc;
+                            const unsigned li = TRANS ? (c[u] & 127u) : lr;
+                            const unsigned k = TRANS ? lr : (c[u] & 127u);
+                            const unsigned q = k >> 2, e = k & 3u;
+                            const unsigned m = s_mask[j * TM_LANES + li];
+                            const size_t pos = (size_t)(s_start[j] - run) + TM_REC_Q + s_off[j * TM_LANES + li] + __popc(m & ((1u << q) - 1u));
+                            const __half hh = __float2half_rn(x[u]);
+                            h_img[pos * 4 + e] = __half_as_ushort(t ? __float2half_rn(x[u] - __half2float(hh)) : hh);
+                        }
+                    }
+                }
+                if (staged) {
+                    __syncthreads();
+                    for (unsigned i = tid; i < c_quads / 2; i += THREADS) reinterpret_cast<uint4*>(qs)[i] = reinterpret_cast<const uint4*>(s_img)[i];
+                }
+                __syncthreads();
+            }
+            if (tid < TM_LANES) s_cur0[tid] = s_cur1[tid];
+            run = s_total;
+            __syncthreads();
         }
     }
 }
@@ -329,7 +364,13 @@ void* tm_build(salg_ctx* ctx, const salg_csr* c, const int64_t* in_ptr, const ui
         // (the tiles of the padding row blocks point at it)
         const size_t q_cap = (size_t)c->nnz + (size_t)n_tiles * (TM_REC_Q + 2) + 2 * TM_REC_Q + 64;
         const uint64_t zero_rec = (uint64_t)((q_cap - TM_REC_Q - 32) & ~(size_t)1);
-        const size_t smem = (size_t)t->n_cb * (TM_LANES * 4 + 4 + TM_LANES * 2);
+        // chunk = as many tiles as fit a ~64 KB image at the operator's average density (three CTAs per SM)
+        const double avg_tile_q = TM_REC_Q + 2.0 + (double)c->nnz / std::max<double>(1.0, (double)n_rb_real * t->n_cb);
+        const unsigned img_quads = 8192;
+        int ch = (int)std::max(1.0, std::min<double>(32.0, std::floor(img_quads * 0.9 / avg_tile_q)));
+        ch = std::min(ch, t->n_cb);
+        const size_t smem_mask = ((size_t)ch * (TM_LANES * 4 + 4 + TM_LANES * 2) + 15) & ~(size_t)15;
+        const size_t smem = smem_mask + (size_t)img_quads * 8;
         for (int o = 0; o < 2; o++) {
             TmFormat& f = o ? t->T : t->R;
             f.info = (uint64_t*)dev_alloc(ctx, (size_t)(n_tiles + 1) * 8);
@@ -343,20 +384,15 @@ void* tm_build(salg_ctx* ctx, const salg_csr* c, const int64_t* in_ptr, const ui
                 ctx->n_launch++;
             }
             if (n_rb_real == 0) continue;
-            const bool wide = smem > 100 * 1024;                 // one CTA per SM: 1024 threads
-            const int per_sm = wide ? 1 : smem > 48 * 1024 ? 2 : 3;
-            const int grid = std::min(n_rb_real, ctx->sm_count * per_sm);
-            auto launch = [&](auto kernel, int threads) {
-                set_max_dyn_smem(kernel, (int)smem);
-                kernel<<<grid, threads, smem, st>>>(in_ptr, in_shift, c->row_ptr, in_col, in_val, c->nrows, n_rb_real, t->n_cb, t->a_terms,
-                                                    t->a_scale, f.info, f.q_hi, f.q_lo);
-            };
+            const int grid = std::min(n_rb_real, ctx->sm_count * 3);
             if (o == 0) {
-                if (wide) launch(tm_build_kernel<false, 1024>, 1024);
-                else launch(tm_build_kernel<false, 512>, 512);
+                set_max_dyn_smem(tm_build_kernel<false>, (int)smem);
+                tm_build_kernel<false><<<grid, TM_BUILD_THREADS, smem, st>>>(in_ptr, in_shift, c->row_ptr, in_col, in_val, c->nrows, n_rb_real,
+                                                                            t->n_cb, t->a_terms, t->a_scale, f.info, f.q_hi, f.q_lo, ch, img_quads);
             } else {
-                if (wide) launch(tm_build_kernel<true, 1024>, 1024);
-                else launch(tm_build_kernel<true, 512>, 512);
+                set_max_dyn_smem(tm_build_kernel<true>, (int)smem);
+                tm_build_kernel<true><<<grid, TM_BUILD_THREADS, smem, st>>>(in_ptr, in_shift, c->row_ptr, in_col, in_val, c->nrows, n_rb_real,
+                                                                           t->n_cb, t->a_terms, t->a_scale, f.info, f.q_hi, f.q_lo, ch, img_quads);
             }
             ctx->n_launch++;
             SALG_CUDA(cudaGetLastError());
