@@ -369,8 +369,8 @@ def run_ours(args, wl):
                for k, v in merged.items()}
     # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the two product kernels from ONE
     # `ncu --set full` capture each, on this workload at 1 GPU (profiles/, see TRAFFIC_SRC)
-    TRAFFIC_SRC = "profiles/r02_ncu_full_tm_products.csv"
-    ncu_traffic = {("cfg3", "spmm"): 1.094948e9 + 0.235534e9, ("cfg3", "spmm_t"): 1.236483e9 + 0.006493e9}
+    TRAFFIC_SRC = "profiles/r02_ncu_full_top_kernels.csv"
+    ncu_traffic = {("cfg3", "spmm"): 1.094799e9 + 0.236912e9, ("cfg3", "spmm_t"): 1.239400e9 + 0.009086e9}
     dom = max((k for k in ("spmm", "spmm_t") if k in prof), key=lambda k: prof[k][0], default=None)
     roofline = None
     if dom:

@@ -23,8 +23,9 @@
  *  - there is no CPU fallback: without a CUDA device every compute entry point fails with
  *    SALG_ERR_CUDA.
  *  - per-GPU size limits: row offsets are 64-bit everywhere, so statistics, Normalize / Log1P, column selection, transform
- *    and the fused masked fit (which only ever tiles the KEPT entries) take shards of any size that fits in memory; the tile
- *    format and the transposed copy index entries with 32 bits, so unmasked f32 fits, f64 fits and Lanczos fits need
+ *    the fused masked fit and — with the default TMEM-operand products, whose tile records are addressed with 64 bits —
+ *    unmasked f32 randomized fits take shards of any size that fits in memory; the transposed copy (f64 fits, Lanczos,
+ *    salg_csr_transpose) and the round-1 dense-tile format (SALG_SPMM_IMPL=tc) index entries with 32 bits and need
  *    < 2^31 stored entries PER GPU SHARD (SALG_ERR_UNSUPPORTED otherwise: shard the rows over more GPUs).
  */
 #ifndef SALG_H
@@ -92,8 +93,9 @@ int salg_ctx_rank(const salg_ctx* ctx, int* rank, int* nranks);
  * start synchronises the stream and records; stop records, waits and returns the elapsed device ms. */
 int salg_timer_start(salg_ctx* ctx);
 int salg_timer_stop(salg_ctx* ctx, double* ms);
-/* Sparse x panel product implementation for f32 operators: 0 = tile-densified tcgen05 kernels (default),
- * 1 = CUDA-core chunk kernels (always used for f64).  Environment default: SALG_SPMM_IMPL=chunk. */
+/* Sparse x panel product implementation for f32 operators: 2 = tcgen05.mma with the sparse operand expanded into tensor
+ * memory (csrc/tm.cu, default), 0 = tcgen05.mma on tiles densified in shared memory (csrc/tc.cu, round 1),
+ * 1 = CUDA-core chunk kernels (always used for f64).  Environment: SALG_SPMM_IMPL=tm | tc | chunk. */
 int salg_ctx_set_spmm_impl(salg_ctx* ctx, int impl);
 /* Number of kernels of this library launched on the context's stream since its creation. */
 int salg_launch_count(salg_ctx* ctx, int64_t* out);

@@ -193,7 +193,7 @@ void spmm_A(salg_ctx* ctx, const salg_csr* c, const T* X, T* out, const double* 
     if constexpr (std::is_same<T, float>::value) {
         // (shards of 2^31 or more stored entries have no tile format: A X falls back to the chunk kernel, whose offsets
         // are 64-bit; A^T Y needs the transposed copy or the tile format, both limited to < 2^31 entries per GPU)
-        if (!pattern && tc_enabled(ctx) && c->nnz < ((int64_t)1 << 31)) {
+        if (!pattern && tc_enabled(ctx) && (ctx->spmm_impl == 2 || c->nnz < ((int64_t)1 << 31))) {
             tc_spmm_A(ctx, c, X, out, corr);
             return;
         }
