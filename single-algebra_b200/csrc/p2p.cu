@@ -1,8 +1,9 @@
 // p2p.cu — one-shot all-reduce of the small replicated operands over NVLink peer memory.
 //
 // Why: the power iteration all-reduces {64 x 64 Gram + column sums (f64), n_eff x 64 partial panel (f32)} once per half step —
-// 0.5 MB at config 3.  Through NCCL that measured ~60 us per call on 8 B200s (latency, 7 GB/s algorithmic bandwidth), 0.64 ms
-// of a 5.95 ms fit; the NVLink wires are idle.  Here every rank owns a buffer that all peers map (CUDA IPC); an all-reduce is
+// 0.5 MB at config 3.  Through NCCL that measured ~60 us per call on 8 B200s (7 GB/s algorithmic bandwidth), 0.64 ms of a
+// 5.95 ms fit.  This file tests whether the collective's own latency is the cost (it is not, see p2p_init): every rank owns a
+// buffer that all peers map (CUDA IPC); an all-reduce is
 // ONE kernel per rank: publish the local operand in the own buffer, raise the own flag (release, system scope), wait for the
 // peers' flags (acquire), then every rank reads all operands over NVLink and sums them IN RANK ORDER — all ranks get
 // bit-identical sums, which the replicated small-side factorisations rely on.  Two alternating halves make reuse safe: a rank
@@ -139,11 +140,12 @@ void p2p_destroy(salg_ctx* ctx) {
 // Collective (every rank of ctx->comm calls it right after ncclCommInitRank).  Leaves ctx->p2p == nullptr on every rank unless
 // every rank could map every peer.
 void p2p_init(salg_ctx* ctx) {
-    // SALG_P2P=0 / 1 forces NCCL / peer memory; default: peer memory from 4 ranks on (at 2 ranks NCCL's own latency is as low:
-    // 28 us against 32 us per half-step all-reduce measured at config 3)
+    // Opt-in (SALG_P2P=1).  Measured at config 3: 32 us per half-step all-reduce against NCCL's 28 us on 2 GPUs, 63 us against
+    // 57 us on 8 — the time of these 0.5 MB all-reduces is the skew between the ranks arriving, not the collective's own
+    // latency, so the library's kernel buys nothing over NCCL here and NCCL stays the default.
     const char* e = getenv("SALG_P2P");
-    const bool want = e ? atoi(e) != 0 : ctx->nranks >= 4;
-    if (ctx->nranks <= 1 || ctx->nranks > P2P_MAX_RANKS || !want || getenv("SALG_NO_P2P")) return;
+    const bool want = e && atoi(e) != 0;
+    if (ctx->nranks <= 1 || ctx->nranks > P2P_MAX_RANKS || !want) return;
     cudaStream_t st = ctx->stream;
     P2P* p = new P2P();
     p->nranks = ctx->nranks;
