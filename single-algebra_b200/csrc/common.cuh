@@ -306,7 +306,8 @@ void tc_free(salg_ctx* owner, void* tiles);
 // tile format of the operator whose row r lives at [in_ptr[r] >> in_shift, ... + c->row_ptr[r+1] - c->row_ptr[r]) of col / val
 // (fused compaction: the kept entries sit at the rows' scaled ORIGINAL offsets); attaches it to c
 void tc_attach_tiles_f32(salg_ctx* ctx, salg_csr* c, const int64_t* in_ptr, int in_shift, const uint32_t* col, const float* val);
-void tc_spmm_A(salg_ctx* ctx, const salg_csr* c, const float* X, float* Y, const double* corr, unsigned* d_amax = nullptr);
+void tc_spmm_A(salg_ctx* ctx, const salg_csr* c, const float* X, float* Y, const double* corr, unsigned* d_amax = nullptr,
+               int b_terms = 2);
 size_t tc_yprep_bytes(salg_ctx* ctx, const salg_csr* c);
 void tc_gram_prep(salg_ctx* ctx, const salg_csr* c, const float* Y, const unsigned* d_amax, uint8_t* Yprep, float* d_scales,
                   double* G /*GRAM_BUF*/);

@@ -401,10 +401,11 @@ static salg_pca* pca_fit(salg_ctx* ctx, const salg_csr* x, const salg_pca_params
                     RiT.alloc(LP * LP, st);
                 }
             }
-            auto product_A = [&](const T* X) {      // Y = A_c X (corr holds mu^T X)
+            static const bool ax_single = getenv("SALG_AX_SINGLE") != nullptr;   // (experiment: 11-bit panel in the inner iterations)
+            auto product_A = [&](const T* X, bool inner = false) {      // Y = A_c X (corr holds mu^T X)
                 if constexpr (std::is_same<T, float>::value) {
                     if (fused) {
-                        tc_spmm_A(ctx, op, X, Y.get(), center ? corr.get() : nullptr, yamax.get());
+                        tc_spmm_A(ctx, op, X, Y.get(), center ? corr.get() : nullptr, yamax.get(), (inner && ax_single) ? 1 : 2);
                         return;
                     }
                 }
@@ -427,7 +428,7 @@ static salg_pca* pca_fit(salg_ctx* ctx, const salg_csr* x, const salg_pca_params
                     }
                     cholqr2<T>(ctx, Z.get(), n_eff, l, false, nullptr, nullptr, d_flag.get(), 1);
                     if (center) panel_colsum<T>(ctx, Z.get(), n_eff, d_mu, corr.get());
-                    product_A(Z.get());
+                    product_A(Z.get(), it + 1 < q);
                     continue;
                 }
                 if (tall_norm) {

@@ -117,7 +117,7 @@ void* tm_build(salg_ctx* ctx, const salg_csr* c, const int64_t* in_ptr, const ui
 int tm_n_rb(const void* tiles);
 int tm_terms(const void* tiles);
 float tm_scale(const void* tiles);
-void tm_spmm_A(salg_ctx* ctx, const salg_csr* c, void* tiles, const float* X, float* Y, const double* corr, unsigned* d_amax);
+void tm_spmm_A(salg_ctx* ctx, const salg_csr* c, void* tiles, const float* X, float* Y, const double* corr, unsigned* d_amax, int b_terms);
 void tm_aty_launch(salg_ctx* ctx, const salg_csr* c, void* tiles, const uint8_t* Yprep, const float* scales, float* Z);
 static bool tm_wanted(const salg_ctx* ctx, const salg_csr* c) { return ctx->spmm_impl == 2 && tm_supported(c); }
 
@@ -1379,14 +1379,14 @@ static void tc_dbg_print(salg_ctx* ctx, const char* what) {
 }
 
 // Y (nrows x 64) = A X - 1 corr^T; d_amax (optional, device, zeroed here) receives the bits of max |Y|
-void tc_spmm_A(salg_ctx* ctx, const salg_csr* c, const float* X, float* Y, const double* corr, unsigned* d_amax) {
+void tc_spmm_A(salg_ctx* ctx, const salg_csr* c, const float* X, float* Y, const double* corr, unsigned* d_amax, int b_terms) {
     cudaStream_t st = ctx->stream;
     TcTiles* t = tiles_of(ctx, c);
     if (c->nrows == 0) return;
     double bytes = (double)c->nnz * 8 + (double)(c->nrows + 1) * 8 + (double)c->ncols * 60 * 4 + (double)c->nrows * 60 * 4;
     ProfScope ps(ctx, PROF_SPMM, bytes);   // includes the panel pre-split
     if (t->tm) {
-        tm_spmm_A(ctx, c, t->tm, X, Y, corr, d_amax);
+        tm_spmm_A(ctx, c, t->tm, X, Y, corr, d_amax, b_terms);
         return;
     }
     DevBuf<uint8_t> Xprep((size_t)t->n_cb * AxSmem::D_BYTES, st);

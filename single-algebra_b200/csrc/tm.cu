@@ -680,6 +680,7 @@ struct TmArgs {
     const double* corr;       // A X
     unsigned* amax_out;       // A X
     int dbg;                  // timing experiments (SALG_TM_DBG bits; results are wrong with a bit >= 2 set)
+    int b_terms;              // A X: fp16 terms of the panel that are multiplied (2 = 22 significant bits, 1 = 11: experiment)
 };
 
 // The serial roles (MMA issuers, loaders) run as CONVERGED warps: every lane walks the same loop, waits on the same barrier,
@@ -935,7 +936,7 @@ tm_product_kernel(const TmArgs g) {
                                 } else {
                                     if (!ATY) {
                                         umma_ts_run8(d_tmem, a_tmem, bd, idesc, first, 128);
-                                        umma_ts_run8(d_tmem, a_tmem, bd + 1024u, idesc, 1u, 128);
+                                        if (g.b_terms > 1) umma_ts_run8(d_tmem, a_tmem, bd + 1024u, idesc, 1u, 128);
                                     } else {
                                         umma_ts_run8(d_tmem, a_tmem, bd, idesc, first, 256);
                                     }
@@ -1090,7 +1091,7 @@ static void tm_dbg_print(salg_ctx* ctx, const char* what) {
 size_t tm_xprep_bytes(const void* tiles) { return (size_t)((const TmTiles*)tiles)->n_cb * TM_STAGE_BYTES; }
 
 // Y (nrows x 64) = A X - 1 corr^T; d_amax (optional, zeroed here) receives the bits of max |Y|
-void tm_spmm_A(salg_ctx* ctx, const salg_csr* c, void* tiles, const float* X, float* Y, const double* corr, unsigned* d_amax) {
+void tm_spmm_A(salg_ctx* ctx, const salg_csr* c, void* tiles, const float* X, float* Y, const double* corr, unsigned* d_amax, int b_terms) {
     cudaStream_t st = ctx->stream;
     TmTiles* t = (TmTiles*)tiles;
     DevBuf<uint8_t> Xprep(tm_xprep_bytes(t), st);
@@ -1116,6 +1117,7 @@ void tm_spmm_A(salg_ctx* ctx, const salg_csr* c, void* tiles, const float* X, fl
     a.out = Y;
     a.corr = corr;
     a.amax_out = d_amax;
+    a.b_terms = b_terms;
     a.dbg = getenv("SALG_TM_DBG") ? atoi(getenv("SALG_TM_DBG")) : 0;
     set_max_dyn_smem(tm_product_kernel<false>, TM_SMEM);
     const int grid = std::min(n_pairs, ctx->sm_count);
