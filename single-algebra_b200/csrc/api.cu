@@ -278,6 +278,8 @@ int salg_ctx_destroy(salg_ctx* c) {
         cudaStreamSynchronize(c->stream);
         prof_collect(c);
         for (auto e : c->event_pool) cudaEventDestroy(e);
+        if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+        if (c->ev_join) cudaEventDestroy(c->ev_join);
         if (c->timer0) cudaEventDestroy(c->timer0);
         if (c->timer1) cudaEventDestroy(c->timer1);
         for (int i = 0; i < salg_ctx::N_STAGE; i++) {

@@ -128,6 +128,8 @@ struct salg_ctx {
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
     void* p2p = nullptr;           // peer-memory all-reduce state (p2p.cu), nullptr = NCCL only
+    int sm_reserve = 0;            // SMs the persistent product kernels leave free (a one-CTA kernel running beside them on another stream)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // fork / join of the side stream (copy_stream) inside a fit
 };
 
 struct salg_csr {
@@ -309,13 +311,22 @@ void tc_attach_tiles_f32(salg_ctx* ctx, salg_csr* c, const int64_t* in_ptr, int 
 void tc_spmm_A(salg_ctx* ctx, const salg_csr* c, const float* X, float* Y, const double* corr, unsigned* d_amax = nullptr,
                int b_terms = 2);
 size_t tc_yprep_bytes(salg_ctx* ctx, const salg_csr* c);
+// no_gram: only the column sums (G + 64*64 ..) and the pre-split operand are produced (the Gram part of G stays zero)
 void tc_gram_prep(salg_ctx* ctx, const salg_csr* c, const float* Y, const unsigned* d_amax, uint8_t* Yprep, float* d_scales,
-                  double* G /*GRAM_BUF*/);
+                  double* G /*GRAM_BUF*/, bool no_gram = false);
 void tc_gram_probe(salg_ctx* ctx, const float* Y, int64_t m, double* G, uint8_t* yprep_out, int iters, double* avg_ms);
 void tc_set_amax(salg_ctx* ctx, unsigned* d_amax, float bound);
 void tc_spmm_At_prepped(salg_ctx* ctx, const salg_csr* c, const uint8_t* Yprep, const float* d_scales, float* Z,
                         const float* mu, const double* corr);
 void tc_spmm_At(salg_ctx* ctx, const salg_csr* c, const float* Y, float* Z, const float* mu, const double* corr);
+// fused small-side step of the power iteration (TMEM-operand products): zside_solve -> tc_zside_apply -> tc_spmm_A_prepped
+bool tc_zside_supported(salg_ctx* ctx, const salg_csr* c);
+size_t tc_xprep_bytes(salg_ctx* ctx, const salg_csr* c);
+float tc_a_scale(salg_ctx* ctx, const salg_csr* c);
+void tc_zside_apply(salg_ctx* ctx, const salg_csr* c, float* Z, const float* d_M, const float* mu, const float* d_scales,
+                    uint8_t* Xprep, double* corr);
+void tc_spmm_A_prepped(salg_ctx* ctx, const salg_csr* c, const uint8_t* Xprep, const float* d_scales, float* Y, const double* corr,
+                       unsigned* d_amax, int b_terms);
 
 // ---- dense.cu -------------------------------------------------------------------------------------
 template <typename T> void panel_gram(salg_ctx* ctx, const T* P, int64_t m, double* d_out /*GRAM_BUF*/);
@@ -331,6 +342,11 @@ template <typename T> void panel_colscale(salg_ctx* ctx, T* P, int64_t m, const 
 template <typename T> void panel_to_rowmajor_t(salg_ctx* ctx, const T* V, int64_t n, int d, T* out /* d x n */);
 template <typename T> void panel_pack(salg_ctx* ctx, const T* src, int64_t m, int k, T* dst);      // (m x k) -> (m x 64) zero padded
 template <typename T> void panel_unpack(salg_ctx* ctx, const T* src, int64_t m, int k, T* dst);    // (m x 64) -> (m x k)
+// dense.cu: Cholesky of Gy, Gram of the raw Z, Cholesky of the transformed Gram -> M = R1^{-1} R2^{-1}, pre-split scale; zeroes corr
+void zside_solve(salg_ctx* ctx, const float* Z, int64_t n, const double* d_Gy, int k, float a_scale, double* d_part,
+                 unsigned* d_ticket, float* d_M, float* d_scales, double* d_corr, int* d_flag);
+size_t zside_part_elems();
+bool zside_two_step();
 template <typename T> void cholqr2(salg_ctx* ctx, T* Y, int64_t m_local, int k, bool sharded, double* d_colsum64,
                                    double* d_Rtot, int* d_flag, int passes);
 

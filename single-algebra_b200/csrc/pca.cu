@@ -346,6 +346,7 @@ static salg_pca* pca_fit(salg_ctx* ctx, const salg_csr* x, const salg_pca_params
         DevBuf<double> d_sign(LP, st);
         std::vector<double> s_host;
         int d_out = rank;
+        bool scores_done = false;
 
         if (prm->svd_method == SALG_SVD_RANDOM) {
             // l = rank + n_oversamples, clamped to the dimensions of the operator: a wider sketch is rank-deficient by
@@ -391,6 +392,11 @@ static salg_pca* pca_fit(salg_ctx* ctx, const salg_csr* x, const salg_pca_params
             DevBuf<unsigned> yamax;
             DevBuf<double> Gy;
             DevBuf<T> RiT;
+            bool zfused = false;
+            DevBuf<double> zpart;
+            DevBuf<unsigned> zticket;
+            DevBuf<float> zM, zscales;
+            DevBuf<uint8_t> zXprep;
             if constexpr (std::is_same<T, float>::value) {
                 fused = tc_enabled(ctx) && tall_norm && q > 0 && !getenv("SALG_NO_FUSED_NORM");
                 if (fused) {
@@ -399,6 +405,16 @@ static salg_pca* pca_fit(salg_ctx* ctx, const salg_csr* x, const salg_pca_params
                     yamax.alloc(1, st);
                     Gy.alloc(GRAM_BUF, st);
                     RiT.alloc(LP * LP, st);
+                    // one launch for the replicated Cholesky / Gram / Cholesky chain of a half step, one for its application
+                    zfused = tc_zside_supported(ctx, op) && !getenv("SALG_NO_ZSIDE");
+                    if (zfused) {
+                        zpart.alloc(zside_part_elems(), st);
+                        zticket.alloc(1, st);
+                        SALG_CUDA(cudaMemsetAsync(zticket.get(), 0, 4, st));
+                        zM.alloc(LP * LP, st);
+                        zscales.alloc(2, st);
+                        zXprep.alloc(tc_xprep_bytes(ctx, op) + 16, st);
+                    }
                 }
             }
             static const bool ax_single = getenv("SALG_AX_SINGLE") != nullptr;   // (experiment: 11-bit panel in the inner iterations)
@@ -419,10 +435,20 @@ static salg_pca* pca_fit(salg_ctx* ctx, const salg_csr* x, const salg_pca_params
                     if constexpr (std::is_same<T, float>::value) {
                         // every rank centres its partial with ITS OWN column sums: sum_r (A_r^T Y_r - mu cs_r^T) is the
                         // centred product, so the Gram / column sums and the partial panel share one NCCL launch
-                        tc_gram_prep(ctx, op, Y.get(), yamax.get(), Yprep.get(), yscales.get(), Gy.get());
+                        tc_gram_prep(ctx, op, Y.get(), yamax.get(), Yprep.get(), yscales.get(), Gy.get(),
+                                     zfused && !zside_two_step());       // (the one-step small side needs no Gram of Y)
                         tc_spmm_At_prepped(ctx, op, Yprep.get(), yscales.get(), Z.get(), d_mu,
                                            center ? Gy.get() + LP * LP : nullptr);
                         allreduce_gram_and_panel(ctx, Gy.get(), GRAM_BUF, Z.get(), (size_t)n_eff * LP);
+                        if (zfused) {
+                            // Z <- orth(Z R1^{-1}) and everything the next A X needs of it (mu^T Z, pre-split operand): 2 launches
+                            zside_solve(ctx, Z.get(), n_eff, Gy.get(), l, tc_a_scale(ctx, op), zpart.get(), zticket.get(), zM.get(),
+                                        zscales.get(), corr.get(), d_flag.get());
+                            tc_zside_apply(ctx, op, Z.get(), zM.get(), center ? d_mu : nullptr, zscales.get(), zXprep.get(), corr.get());
+                            tc_spmm_A_prepped(ctx, op, zXprep.get(), zscales.get(), Y.get(), center ? corr.get() : nullptr, yamax.get(),
+                                              (it + 1 < q && ax_single) ? 1 : 2);
+                            continue;
+                        }
                         chol_inv<T>(ctx, Gy.get(), l, nullptr, nullptr, RiT.get(), d_flag.get());
                         panel_mul<T>(ctx, Z.get(), n_eff, RiT.get(), Z.get());
                     }
@@ -473,11 +499,54 @@ static salg_pca* pca_fit(salg_ctx* ctx, const salg_csr* x, const salg_pca_params
             }
             // B^T = Q_B R_B; R_B = U_R S V_R^T
             cholqr2<T>(ctx, Z.get(), n_eff, l, false, nullptr, Rb.get(), d_flag.get(), 2);
-            jacobi_svd64(ctx, Rb.get(), l, Ur.get(), Sr.get(), Vr.get(), d_flag.get());
+            // fit_transform on the TMEM-operand path: the scores are A_c V = (A_c Q_B) U_R diag(sign), so the big product
+            // A_c Q_B does not have to wait for the one-CTA Jacobi SVD — it runs beside it (the SVD on the side stream, the
+            // persistent product kernel on one SM less) and only a rows x 64 by 64 x 64 product is left afterwards.
+            bool tail_overlap = false;
+            if constexpr (std::is_same<T, float>::value)
+                tail_overlap = prm->keep_scores && fused && zfused && op->nrows > 0 && !getenv("SALG_NO_TAIL_OVERLAP");
+            if (tail_overlap) {
+                if (!ctx->ev_fork) {
+                    SALG_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+                    SALG_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+                }
+                SALG_CUDA(cudaEventRecord(ctx->ev_fork, st));
+                SALG_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fork, 0));
+                ctx->stream = ctx->copy_stream;
+                try {
+                    jacobi_svd64(ctx, Rb.get(), l, Ur.get(), Sr.get(), Vr.get(), d_flag.get());
+                } catch (...) {
+                    ctx->stream = st;
+                    throw;
+                }
+                ctx->stream = st;
+                SALG_CUDA(cudaEventRecord(ctx->ev_join, ctx->copy_stream));
+                try {
+                    P->d_scores = dev_alloc(ctx, (size_t)op->nrows * LP * sizeof(T));
+                    if constexpr (std::is_same<T, float>::value) {
+                        if (center) panel_colsum<T>(ctx, Z.get(), n_eff, d_mu, corr.get());
+                        ctx->sm_reserve = 1;
+                        tc_spmm_A(ctx, op, Z.get(), (float*)P->d_scores, center ? corr.get() : nullptr);
+                        ctx->sm_reserve = 0;
+                    }
+                    SALG_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+                } catch (...) {
+                    ctx->sm_reserve = 0;
+                    cudaStreamSynchronize(ctx->copy_stream);     // the side stream still reads this function's buffers
+                    throw;
+                }
+            } else {
+                jacobi_svd64(ctx, Rb.get(), l, Ur.get(), Sr.get(), Vr.get(), d_flag.get());
+            }
             cast_mat64<T>(ctx, Ur.get(), M64.get(), nullptr);
             panel_mul<T>(ctx, Z.get(), n_eff, M64.get(), d_V);                 // V = Q_B U_R
             flip_find<T>(ctx, d_V, n_eff, d_sign.get());
             panel_colscale<T>(ctx, d_V, n_eff, d_sign.get());
+            if (tail_overlap) {
+                cast_mat64<T>(ctx, Ur.get(), M64.get(), d_sign.get());         // U_R diag(sign)
+                panel_mul<T>(ctx, (const T*)P->d_scores, op->nrows, M64.get(), (T*)P->d_scores);
+                scores_done = true;
+            }
             s_host.resize(LP);
             SALG_CUDA(cudaMemcpyAsync(s_host.data(), Sr.get(), LP * 8, cudaMemcpyDeviceToHost, st));
             SALG_CUDA(cudaStreamSynchronize(st));
@@ -496,7 +565,7 @@ static salg_pca* pca_fit(salg_ctx* ctx, const salg_csr* x, const salg_pca_params
             panel_colscale<T>(ctx, d_V, n_eff, d_sign.get());
             SALG_CUDA(cudaStreamSynchronize(st));
         }
-        if (prm->keep_scores) {
+        if (prm->keep_scores && !scores_done) {
             // fit_transform = fit, then transform of the same rows (pca/sparse/mod.rs:355-358):
             // (X - 1 mu^T) V on the kept columns, computed while the compacted operator is still resident.
             // (U S from the factorisation is only the projection of this onto range(Q).)

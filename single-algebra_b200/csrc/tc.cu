@@ -119,6 +119,11 @@ int tm_terms(const void* tiles);
 float tm_scale(const void* tiles);
 void tm_spmm_A(salg_ctx* ctx, const salg_csr* c, void* tiles, const float* X, float* Y, const double* corr, unsigned* d_amax, int b_terms);
 void tm_aty_launch(salg_ctx* ctx, const salg_csr* c, void* tiles, const uint8_t* Yprep, const float* scales, float* Z);
+void tm_spmm_A_prepped(salg_ctx* ctx, const salg_csr* c, void* tiles, const uint8_t* Xprep, const float* scales, float* Y,
+                       const double* corr, unsigned* d_amax, int b_terms);
+void tm_zside_apply(salg_ctx* ctx, const salg_csr* c, void* tiles, float* Z, const float* d_M, const float* mu, const float* scales,
+                    uint8_t* Xprep, double* corr);
+size_t tm_xprep_bytes(const void* tiles);
 static bool tm_wanted(const salg_ctx* ctx, const salg_csr* c) { return ctx->spmm_impl == 2 && tm_supported(c); }
 
 void tc_free(salg_ctx* owner, void* p) {
@@ -1121,7 +1126,7 @@ tc_gram_prep_kernel(const float* __restrict__ Y, int64_t m, int n_rb, const floa
                 const uint32_t d_tmem = tmem_base + (uint32_t)as * 128u;
                 // K = 128 rows: eight K-steps of 16, both operands are the SAME buffer (P P^T)
                 const uint64_t desc = desc0 + (uint64_t)ob * (GpSmem::OP_BYTES >> 4);
-                if (!(dbg & 2)) {                                             // (timing experiment: no MMA)
+                if (!(dbg & (2 | 32))) {                                      // (2: timing experiment, 32: caller needs no Gram)
                     umma_f16_run4(d_tmem, desc, desc, idesc, (it % GP_DRAIN) != 0, 256, 256);
                     umma_f16_run4(d_tmem, desc + 1024, desc + 1024, idesc, 1, 256, 256);
                 }
@@ -1138,7 +1143,7 @@ tc_gram_prep_kernel(const float* __restrict__ Y, int64_t m, int n_rb, const floa
             mbar_wait_warp(&acc_full[as], (grp >> 1) & 1, lane);
             tc_fence_after();
 #pragma unroll 1
-            for (int c4 = 0; c4 < 4; c4++) {
+            for (int c4 = 0; c4 < ((dbg & 32) ? 0 : 4); c4++) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)as * 128u + c4 * 32, v);
 #pragma unroll
@@ -1152,7 +1157,7 @@ tc_gram_prep_kernel(const float* __restrict__ Y, int64_t m, int n_rb, const floa
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_free[as]);
         }
-        if (n_mine > 0 && !(lane & 1)) {
+        if (n_mine > 0 && !(lane & 1) && !(dbg & 32)) {
             const double s = (double)scales[0];
             const double inv_s2 = 1.0 / (s * s);
             for (int cc = 0; cc < LP; cc++) {
@@ -1405,6 +1410,25 @@ void tc_spmm_A(salg_ctx* ctx, const salg_csr* c, const float* X, float* Y, const
     tc_dbg_print(ctx, "ax");
 }
 
+// ---- fused small-side step (TMEM-operand generation only): zside_solve (dense.cu) -> tc_zside_apply -> tc_spmm_A_prepped ----
+bool tc_zside_supported(salg_ctx* ctx, const salg_csr* c) { return tiles_of(ctx, c)->tm != nullptr; }
+size_t tc_xprep_bytes(salg_ctx* ctx, const salg_csr* c) { return tm_xprep_bytes(tiles_of(ctx, c)->tm); }
+float tc_a_scale(salg_ctx* ctx, const salg_csr* c) { return tiles_of(ctx, c)->a_scale; }
+void tc_zside_apply(salg_ctx* ctx, const salg_csr* c, float* Z, const float* d_M, const float* mu, const float* d_scales,
+                    uint8_t* Xprep, double* corr) {
+    TcTiles* t = tiles_of(ctx, c);
+    ProfScope ps(ctx, PROF_PANELMUL, 2.0 * (double)c->ncols * 60 * 4);
+    tm_zside_apply(ctx, c, t->tm, Z, d_M, mu, d_scales, Xprep, corr);
+}
+void tc_spmm_A_prepped(salg_ctx* ctx, const salg_csr* c, const uint8_t* Xprep, const float* d_scales, float* Y, const double* corr,
+                       unsigned* d_amax, int b_terms) {
+    TcTiles* t = tiles_of(ctx, c);
+    if (c->nrows == 0) return;
+    double bytes = (double)c->nnz * 8 + (double)(c->nrows + 1) * 8 + (double)c->ncols * 60 * 4 + (double)c->nrows * 60 * 4;
+    ProfScope ps(ctx, PROF_SPMM, bytes);
+    tm_spmm_A_prepped(ctx, c, t->tm, Xprep, d_scales, Y, corr, d_amax, b_terms);
+}
+
 // Fused pass over a tall panel Y (c->nrows x 64): Yprep = canonical two-term fp16 operand of Y (scale from d_amax, the
 // bits of max |Y| written by tc_spmm_A), d_scales = {s, 1 / (s a_scale)}, G (GRAM_BUF f64) = [Y^T Y, 1^T Y] (local rows).
 size_t tc_yprep_bytes(salg_ctx* ctx, const salg_csr* c) { return (size_t)tiles_of(ctx, c)->n_rb * AtySmem::D_BYTES; }
@@ -1418,7 +1442,7 @@ void tc_set_amax(salg_ctx* ctx, unsigned* d_amax, float bound) {
     SALG_CUDA(cudaGetLastError());
 }
 void tc_gram_prep(salg_ctx* ctx, const salg_csr* c, const float* Y, const unsigned* d_amax, uint8_t* Yprep, float* d_scales,
-                  double* G) {
+                  double* G, bool no_gram) {
     cudaStream_t st = ctx->stream;
     TcTiles* t = tiles_of(ctx, c);
     SALG_CUDA(cudaMemsetAsync(G, 0, GRAM_BUF * sizeof(double), st));
@@ -1429,7 +1453,7 @@ void tc_gram_prep(salg_ctx* ctx, const salg_csr* c, const float* Y, const unsign
     const int n_rb_real = (int)ceil_div(c->nrows, TC_RB);
     set_max_dyn_smem(tc_gram_prep_kernel, (int)(GpSmem::TOTAL));
     int grid = n_rb_real < ctx->sm_count ? n_rb_real : ctx->sm_count;
-    tc_gram_prep_kernel<<<grid, GP_THREADS, GpSmem::TOTAL, st>>>(Y, c->nrows, n_rb_real, d_scales, Yprep, G, 0);
+    tc_gram_prep_kernel<<<grid, GP_THREADS, GpSmem::TOTAL, st>>>(Y, c->nrows, n_rb_real, d_scales, Yprep, G, no_gram ? 32 : 0);
     ctx->n_launch++;
     SALG_CUDA(cudaGetLastError());
 }

@@ -324,6 +324,181 @@ tm_build_kernel(const int64_t* __restrict__ in_ptr, int in_shift, const int64_t*
     }
 }
 
+// ---- second builder: BOTH orientations of a row block's tiles in one pass over its entries, through dense tile images ----------
+// The first builder turns every entry into a shared-memory atomic (quad masks) and, in a second sweep, a 2-byte store at a
+// position looked up from three shared-memory tables, once per orientation: ~250 thread instructions per entry and orientation
+// (ncu: 1.08e9 warp instructions per orientation at config 3, 1.4-1.5 ms each).  Here a chunk of TB2_CH column blocks is built
+// for both orientations at once:
+//   scatter  warps walk their rows' entries of the chunk (coalesced loads, all of a warp's rows in flight) and drop every value
+//            into TWO zeroed dense fp16 images of its 128 x 128 tile, [row][k = column] and [column][k = row]
+//   scan     one thread per (tile, orientation, lane) reads the lane's 32 quads (8 B each) of its image into registers: the non-zero
+//            ones ARE the lane's quads in k order, their pattern the quad mask; a prefix sum over the 128 lanes gives the offsets; the
+//            record is put together in shared memory and leaves with coalesced 16-byte stores.  The lane re-zeroes what it took.
+// An entry costs two 2-byte stores, a quad one 8-byte load and store; both orientations share the loads of the entries.
+// Values whose fp16 image is zero (stored zeros, |x| below 2^-25 of the scale) drop out of the format: they contribute nothing.
+constexpr int TB2_THREADS = 512;
+constexpr int TB2_CH = 2;                                       // column blocks per chunk: TB2_CH x 2 orientations x 128 lanes = threads
+constexpr int TB2_PITCH = 264;                                  // bytes per image row: 128 fp16 + 8 (conflict-free 8-byte reads down a column of lanes)
+constexpr int TB2_IMG = TM_LANES * TB2_PITCH;
+constexpr int TB2_STAGE_QUADS = 1536;                           // payload quads of a staged record; denser tiles store straight to global
+constexpr int TB2_STAGE_BYTES = TM_REC + TB2_STAGE_QUADS * 8;
+constexpr int TB2_SMEM = TB2_CH * 2 * (TB2_IMG + TB2_STAGE_BYTES);
+constexpr int TB2_RPW = TM_LANES / (TB2_THREADS / 32);          // rows per warp
+static_assert(TB2_THREADS == TB2_CH * 2 * TM_LANES, "one scan thread per (tile of the chunk, orientation, lane)");
+static_assert(TB2_STAGE_BYTES % 16 == 0 && TB2_IMG % 16 == 0, "alignment of the staging areas");
+static_assert(TB2_SMEM <= 220 * 1024, "shared memory");
+
+__global__ void __launch_bounds__(TB2_THREADS, 1)
+tm_build2_kernel(const int64_t* __restrict__ in_ptr, int in_shift, const int64_t* __restrict__ ptr, const uint32_t* __restrict__ col,
+                 const float* __restrict__ val, int64_t nrows, int n_rb_real, int n_cb, int terms, float a_scale,
+                 uint64_t* __restrict__ info_r, uint2* __restrict__ r_hi, uint2* __restrict__ r_lo,
+                 uint64_t* __restrict__ info_t, uint2* __restrict__ t_hi, uint2* __restrict__ t_lo) {
+    extern __shared__ __align__(16) uint8_t tb2_sm[];
+    uint8_t* images = tb2_sm;                                   // [tile j][orientation o] -> images + (2 j + o) * TB2_IMG
+    uint8_t* stages = tb2_sm + TB2_CH * 2 * TB2_IMG;            // same indexing, TB2_STAGE_BYTES each
+    __shared__ long long s_row[TM_LANES];
+    __shared__ int s_len[TM_LANES], s_cur[TM_LANES];
+    __shared__ unsigned s_wsum[TB2_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grp = tid >> 7, li = tid & 127;                   // scan role: group = 2 j + o (4 warps each), lane li
+    const int my_j = grp >> 1, my_o = grp & 1;
+    for (int i = tid; i < TB2_CH * 2 * TB2_IMG / 16; i += TB2_THREADS) reinterpret_cast<uint4*>(images)[i] = make_uint4(0u, 0u, 0u, 0u);
+    uint8_t* my_img = images + grp * TB2_IMG;
+    uint8_t* my_stage = stages + grp * TB2_STAGE_BYTES;
+    uint64_t* my_info = my_o ? info_t : info_r;
+    for (int rb = blockIdx.x; rb < n_rb_real; rb += gridDim.x) {
+        const int64_t r0 = (int64_t)rb * TM_LANES;
+        const int64_t qbase = tm_region(ptr[r0], rb, n_cb);
+        unsigned run = 0;                                       // quads of the block's region used so far by MY orientation (even)
+        __syncthreads();
+        if (tid < TM_LANES) {
+            const int64_t r = r0 + tid;
+            s_row[tid] = r < nrows ? (long long)(in_ptr[r] >> in_shift) : 0;
+            s_len[tid] = r < nrows ? (int)(ptr[r + 1] - ptr[r]) : 0;
+            s_cur[tid] = 0;
+        }
+        __syncthreads();
+        for (int jc = 0; jc < n_cb; jc += TB2_CH) {
+            const int nt = jc + TB2_CH < n_cb ? TB2_CH : n_cb - jc;
+            const unsigned c_end = (unsigned)(jc + nt) * TM_DEPTH;
+            unsigned mask0 = 0, off0 = 0, tot0 = 0, start0 = 0, adv = 0;
+            for (int t = 0; t < terms; t++) {
+                // ---- scatter: warp w takes rows w, w + 16, ...; first batches of all its rows in flight together
+                {
+                    unsigned c[TB2_RPW];
+                    float x[TB2_RPW];
+#pragma unroll
+                    for (int i = 0; i < TB2_RPW; i++) {
+                        const int lr = warp + (TB2_THREADS / 32) * i;
+                        const int q = s_cur[lr] + lane;
+                        const bool ok = q < s_len[lr];
+                        c[i] = ok ? col[s_row[lr] + q] : 0xFFFFFFFFu;
+                        x[i] = ok ? val[s_row[lr] + q] : 0.f;
+                    }
+#pragma unroll
+                    for (int i = 0; i < TB2_RPW; i++) {
+                        const int lr = warp + (TB2_THREADS / 32) * i;
+                        unsigned cc = c[i];
+                        float xx = x[i];
+                        int taken = 0, q0 = s_cur[lr];
+                        while (true) {
+                            const bool in_chunk = cc < c_end;                    // (absent entries compare false)
+                            const unsigned bal = __ballot_sync(0xFFFFFFFFu, in_chunk);
+                            if (in_chunk) {
+                                const float xs = xx * a_scale;
+                                const __half hh = __float2half_rn(xs);
+                                const unsigned short h = __half_as_ushort(t ? __float2half_rn(xs - __half2float(hh)) : hh);
+                                const unsigned j = (cc >> 7) - (unsigned)jc, k = cc & 127u;
+                                uint8_t* im = images + (2u * j) * TB2_IMG;
+                                *reinterpret_cast<unsigned short*>(im + (unsigned)lr * TB2_PITCH + k * 2u) = h;
+                                *reinterpret_cast<unsigned short*>(im + TB2_IMG + k * TB2_PITCH + (unsigned)lr * 2u) = h;
+                            }
+                            taken += __popc(bal);
+                            if (bal != 0xFFFFFFFFu) break;                       // a shorter batch met the chunk's (or the row's) end
+                            q0 += 32;
+                            const int q = q0 + lane;
+                            const bool ok = q < s_len[lr];
+                            cc = ok ? col[s_row[lr] + q] : 0xFFFFFFFFu;
+                            xx = ok ? val[s_row[lr] + q] : 0.f;
+                        }
+                        if (t == terms - 1 && lane == 0) s_cur[lr] += taken;
+                    }
+                }
+                __syncthreads();
+                // ---- scan: thread = lane li of (tile my_j, orientation my_o)
+                const bool have = my_j < nt;
+                uint2 q[32];
+                unsigned nz = 0;
+                if (have) {
+#pragma unroll
+                    for (int i = 0; i < 32; i++) q[i] = *reinterpret_cast<const uint2*>(my_img + li * TB2_PITCH + i * 8);
+#pragma unroll
+                    for (int i = 0; i < 32; i++) nz |= ((q[i].x | q[i].y) != 0u ? 1u : 0u) << i;
+#pragma unroll
+                    for (int i = 0; i < 32; i++)
+                        if ((nz >> i) & 1u) *reinterpret_cast<uint2*>(my_img + li * TB2_PITCH + i * 8) = make_uint2(0u, 0u);
+                }
+                if (t == 0) {
+                    mask0 = nz;
+                    const unsigned cnt = (unsigned)__popc(nz);
+                    unsigned incl = cnt;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const unsigned v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                        if (lane >= o) incl += v;
+                    }
+                    if (lane == 31) s_wsum[warp] = incl;
+                    __syncthreads();
+                    unsigned base = 0, tot = 0, tot_first = 0;               // tot_first: quads of tile 0 of the chunk in MY orientation
+#pragma unroll
+                    for (int w = 0; w < 4; w++) {
+                        const unsigned v = s_wsum[grp * 4 + w];
+                        if (grp * 4 + w < warp) base += v;
+                        tot += v;
+                        tot_first += s_wsum[my_o * 4 + w];
+                    }
+                    off0 = base + incl - cnt;
+                    tot0 = tot;
+                    const unsigned rec_first = TM_REC_Q + ((tot_first + 1u) & ~1u);
+                    start0 = run + (my_j ? rec_first : 0u);
+                    // this chunk's advance of MY orientation's region: tile 0's record, and tile 1's when the chunk has one
+                    unsigned tot_second = 0;
+#pragma unroll
+                    for (int w = 0; w < 4; w++) tot_second += s_wsum[(2 + my_o) * 4 + w];
+                    adv = rec_first + (nt > 1 ? TM_REC_Q + ((tot_second + 1u) & ~1u) : 0u);
+                    if (have && li == 0) my_info[(int64_t)rb * n_cb + jc + my_j] = (uint64_t)(qbase + start0) | ((uint64_t)tot << 40);
+                }
+                const bool staged = tot0 <= (unsigned)TB2_STAGE_QUADS;             // uniform over the group's 128 threads
+                uint2* g_rec = (my_o ? (t ? t_lo : t_hi) : (t ? r_lo : r_hi)) + qbase + start0;
+                if (have) {
+                    uint8_t* rec = staged ? my_stage : reinterpret_cast<uint8_t*>(g_rec);
+                    reinterpret_cast<uint32_t*>(rec + 16)[li] = mask0;
+                    reinterpret_cast<unsigned short*>(rec + 16 + 512)[li] = (unsigned short)off0;
+                    if (li == TM_LANES - 1) {
+                        *reinterpret_cast<unsigned long long*>(rec) = (unsigned long long)(qbase + start0 + TM_REC_Q);
+                        *reinterpret_cast<uint2*>(rec + 8) = make_uint2(tot0, 0u);
+                        if (tot0 & 1u) reinterpret_cast<uint2*>(rec + TM_REC)[tot0] = make_uint2(0u, 0u);   // pad to an even quad count
+                    }
+                    uint2* pay = reinterpret_cast<uint2*>(rec + TM_REC) + off0;
+#pragma unroll
+                    for (int i = 0; i < 32; i++)
+                        if ((mask0 >> i) & 1u) pay[__popc(mask0 & ((1u << i) - 1u))] = q[i];
+                }
+                __syncthreads();
+                // ---- staged records leave with coalesced 16-byte stores (each group copies its own)
+                if (have && staged) {
+                    const unsigned n16 = (TM_REC_Q + ((tot0 + 1u) & ~1u)) / 2;
+                    uint4* dst = reinterpret_cast<uint4*>(g_rec);
+                    const uint4* src = reinterpret_cast<const uint4*>(my_stage);
+                    for (unsigned i = li; i < n16; i += TM_LANES) dst[i] = src[i];
+                }
+                // (the next scatter only touches the images; the next record is staged after another barrier)
+            }
+            run += adv;
+        }
+    }
+}
+
 __global__ void tm_fill_u64_kernel(uint64_t* p, int64_t n, uint64_t v) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -371,6 +546,7 @@ void* tm_build(salg_ctx* ctx, const salg_csr* c, const int64_t* in_ptr, const ui
         ch = std::min(ch, t->n_cb);
         const size_t smem_mask = ((size_t)ch * (TM_LANES * 4 + 4 + TM_LANES * 2) + 15) & ~(size_t)15;
         const size_t smem = smem_mask + (size_t)img_quads * 8;
+        static const bool first_builder = getenv("SALG_TM_BUILD") && atoi(getenv("SALG_TM_BUILD")) == 1;
         for (int o = 0; o < 2; o++) {
             TmFormat& f = o ? t->T : t->R;
             f.info = (uint64_t*)dev_alloc(ctx, (size_t)(n_tiles + 1) * 8);
@@ -383,7 +559,7 @@ void* tm_build(salg_ctx* ctx, const salg_csr* c, const int64_t* in_ptr, const ui
                 tm_fill_u64_kernel<<<(unsigned)ceil_div(n_pad, 256), 256, 0, st>>>(f.info + (size_t)n_rb_real * t->n_cb, n_pad, zero_rec);
                 ctx->n_launch++;
             }
-            if (n_rb_real == 0) continue;
+            if (n_rb_real == 0 || !first_builder) continue;
             const int grid = std::min(n_rb_real, ctx->sm_count * 3);
             if (o == 0) {
                 set_max_dyn_smem(tm_build_kernel<false>, (int)smem);
@@ -394,6 +570,16 @@ void* tm_build(salg_ctx* ctx, const salg_csr* c, const int64_t* in_ptr, const ui
                 tm_build_kernel<true><<<grid, TM_BUILD_THREADS, smem, st>>>(in_ptr, in_shift, c->row_ptr, in_col, in_val, c->nrows, n_rb_real,
                                                                            t->n_cb, t->a_terms, t->a_scale, f.info, f.q_hi, f.q_lo, ch, img_quads);
             }
+            ctx->n_launch++;
+            SALG_CUDA(cudaGetLastError());
+        }
+        if (n_rb_real > 0 && !first_builder) {
+            // both orientations in one pass (dense tile images); SALG_TM_BUILD=1 selects the first builder
+            set_max_dyn_smem(tm_build2_kernel, TB2_SMEM);
+            const int grid = std::min(n_rb_real, ctx->sm_count);
+            tm_build2_kernel<<<grid, TB2_THREADS, TB2_SMEM, st>>>(in_ptr, in_shift, c->row_ptr, in_col, in_val, c->nrows, n_rb_real, t->n_cb,
+                                                                  t->a_terms, t->a_scale, t->R.info, t->R.q_hi, t->R.q_lo, t->T.info,
+                                                                  t->T.q_hi, t->T.q_lo);
             ctx->n_launch++;
             SALG_CUDA(cudaGetLastError());
         }
@@ -426,6 +612,73 @@ tm_prep_x_kernel(const float* __restrict__ P, int64_t n, const float* __restrict
 #pragma unroll
     for (int j = 0; j < 8; j++) {
         const float x = tile[o * 8 + j][c];
+        const __half h = __float2half_rn(x);
+        hi[j] = __half_as_ushort(h);
+        lo[j] = __half_as_ushort(__float2half_rn(x - __half2float(h)));
+    }
+    uint8_t* dst = out + (size_t)b * TM_STAGE_BYTES + chunk * 1024u + (uint32_t)(c >> 3) * 128u + (uint32_t)(c & 7) * 16u;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0] | ((uint32_t)hi[1] << 16), hi[2] | ((uint32_t)hi[3] << 16),
+                                                hi[4] | ((uint32_t)hi[5] << 16), hi[6] | ((uint32_t)hi[7] << 16));
+    *reinterpret_cast<uint4*>(dst + 16384) = make_uint4(lo[0] | ((uint32_t)lo[1] << 16), lo[2] | ((uint32_t)lo[3] << 16),
+                                                        lo[4] | ((uint32_t)lo[5] << 16), lo[6] | ((uint32_t)lo[7] << 16));
+}
+
+// ---- the apply half of the fused small-side step (dense.cu: zside_solve_kernel): Z2 = Z0 M for 32 panel rows per CTA, then,
+//      from the same shared-memory tile, (i) Z2 itself, (ii) corr += mu^T Z2 (the centring term of the next A X) and (iii) the
+//      pre-split operand of the next A X exactly as tm_prep_x_kernel writes it.  In place (Z2 == Z0) allowed. ----------------
+__global__ void __launch_bounds__(256)
+tm_zside_apply_kernel(const float* Z0, int64_t n, const float* __restrict__ M, const float* __restrict__ mu,
+                      const float* __restrict__ scales, float* Z2, uint8_t* __restrict__ out, double* __restrict__ corr) {
+    __shared__ __align__(16) float Ms[LP][LP];
+    __shared__ __align__(16) float Pt[LP][32 + 2];        // transposed input tile: Pt[k][row]
+    __shared__ float tile[32][LP + 1];
+    const int tid = threadIdx.x;
+    const int64_t k0 = (int64_t)blockIdx.x * 32;
+    for (int i = tid; i < LP * LP; i += 256) Ms[i >> 6][i & 63] = M[i];
+    for (int i = tid; i < 32 * LP; i += 256) {
+        const int r = i >> 6, c = i & 63;
+        Pt[c][r] = (k0 + r < n) ? Z0[(k0 + r) * LP + c] : 0.f;
+    }
+    __syncthreads();
+    {
+        const int ty = tid >> 4, tx = tid & 15;           // rows 2 ty, 2 ty + 1; columns 4 tx .. 4 tx + 3
+        float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll 8
+        for (int kk = 0; kk < LP; kk++) {
+            const float2 av = *reinterpret_cast<const float2*>(&Pt[kk][2 * ty]);
+            const float4 bv = *reinterpret_cast<const float4*>(&Ms[kk][4 * tx]);
+            const float b[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int y = 0; y < 4; y++) {
+                acc[0][y] = fmaf(av.x, b[y], acc[0][y]);
+                acc[1][y] = fmaf(av.y, b[y], acc[1][y]);
+            }
+        }
+#pragma unroll
+        for (int x = 0; x < 2; x++)
+#pragma unroll
+            for (int y = 0; y < 4; y++) tile[2 * ty + x][4 * tx + y] = acc[x][y];
+    }
+    __syncthreads();
+    for (int i = tid; i < 32 * LP; i += 256) {
+        const int r = i >> 6, c = i & 63;
+        if (k0 + r < n) Z2[(k0 + r) * LP + c] = tile[r][c];
+    }
+    if (mu && tid < LP) {
+        double sacc = 0.0;
+        for (int r = 0; r < 32; r++)
+            if (k0 + r < n) sacc = fma((double)mu[k0 + r], (double)tile[r][tid], sacc);
+        if (sacc != 0.0) atomicAdd(&corr[tid], sacc);
+    }
+    const float s = scales[0];
+    const int o = tid >> 6, c = tid & 63;                  // K-octet of the 32 rows, panel column
+    const int64_t kc0 = k0 + o * 8;
+    const int64_t b = kc0 >> 7;
+    const uint32_t chunk = (uint32_t)(kc0 & 127) >> 3;
+    unsigned short hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const float x = tile[o * 8 + j][c] * s;
         const __half h = __float2half_rn(x);
         hi[j] = __half_as_ushort(h);
         lo[j] = __half_as_ushort(__float2half_rn(x - __half2float(h)));
@@ -1090,17 +1343,12 @@ static void tm_dbg_print(salg_ctx* ctx, const char* what) {
 
 size_t tm_xprep_bytes(const void* tiles) { return (size_t)((const TmTiles*)tiles)->n_cb * TM_STAGE_BYTES; }
 
-// Y (nrows x 64) = A X - 1 corr^T; d_amax (optional, zeroed here) receives the bits of max |Y|
-void tm_spmm_A(salg_ctx* ctx, const salg_csr* c, void* tiles, const float* X, float* Y, const double* corr, unsigned* d_amax, int b_terms) {
+// Y (nrows x 64) = A X - 1 corr^T with X given pre-split (tm_prep_x_kernel / tm_zside_apply_kernel layout, scales = {s, 1 / (s a_scale)});
+// d_amax (optional, zeroed here) receives the bits of max |Y|
+void tm_spmm_A_prepped(salg_ctx* ctx, const salg_csr* c, void* tiles, const uint8_t* Xprep, const float* scales, float* Y,
+                       const double* corr, unsigned* d_amax, int b_terms) {
     cudaStream_t st = ctx->stream;
     TmTiles* t = (TmTiles*)tiles;
-    DevBuf<uint8_t> Xprep(tm_xprep_bytes(t), st);
-    DevBuf<float> scales(2, st);
-    DevBuf<unsigned> amax(1, st);
-    tc_panel_scales(ctx, X, c->ncols, t->a_scale, scales.get(), amax.get());
-    tm_prep_x_kernel<<<(unsigned)(t->n_cb * (TM_DEPTH / 32)), 256, 0, st>>>(X, c->ncols, scales.get(), Xprep.get());
-    ctx->n_launch++;
-    SALG_CUDA(cudaGetLastError());
     if (d_amax) SALG_CUDA(cudaMemsetAsync(d_amax, 0, 4, st));
     TmArgs a{};
     a.info = t->R.info;
@@ -1112,19 +1360,43 @@ void tm_spmm_A(salg_ctx* ctx, const salg_csr* c, void* tiles, const float* X, fl
     const int n_pairs = (int)ceil_div(ceil_div(c->nrows, TM_LANES), 2);
     a.n_units = n_pairs;
     a.n_out = c->nrows;
-    a.prep = Xprep.get();
-    a.scales = scales.get();
+    a.prep = Xprep;
+    a.scales = scales;
     a.out = Y;
     a.corr = corr;
     a.amax_out = d_amax;
     a.b_terms = b_terms;
     a.dbg = getenv("SALG_TM_DBG") ? atoi(getenv("SALG_TM_DBG")) : 0;
     set_max_dyn_smem(tm_product_kernel<false>, TM_SMEM);
-    const int grid = std::min(n_pairs, ctx->sm_count);
+    const int grid = std::min(n_pairs, std::max(1, ctx->sm_count - ctx->sm_reserve));
     tm_product_kernel<false><<<grid, TM_THREADS, TM_SMEM, st>>>(a);
     ctx->n_launch++;
     SALG_CUDA(cudaGetLastError());
     tm_dbg_print(ctx, "ax");
+}
+
+// Y (nrows x 64) = A X - 1 corr^T; d_amax (optional, zeroed here) receives the bits of max |Y|
+void tm_spmm_A(salg_ctx* ctx, const salg_csr* c, void* tiles, const float* X, float* Y, const double* corr, unsigned* d_amax, int b_terms) {
+    cudaStream_t st = ctx->stream;
+    TmTiles* t = (TmTiles*)tiles;
+    DevBuf<uint8_t> Xprep(tm_xprep_bytes(t), st);
+    DevBuf<float> scales(2, st);
+    DevBuf<unsigned> amax(1, st);
+    tc_panel_scales(ctx, X, c->ncols, t->a_scale, scales.get(), amax.get());
+    tm_prep_x_kernel<<<(unsigned)(t->n_cb * (TM_DEPTH / 32)), 256, 0, st>>>(X, c->ncols, scales.get(), Xprep.get());
+    ctx->n_launch++;
+    SALG_CUDA(cudaGetLastError());
+    tm_spmm_A_prepped(ctx, c, tiles, Xprep.get(), scales.get(), Y, corr, d_amax, b_terms);
+}
+
+// the apply half of the fused small-side step: Z (n_eff x 64) <- Z M, corr (zeroed by zside_solve) += mu^T Z, Xprep = pre-split Z
+void tm_zside_apply(salg_ctx* ctx, const salg_csr* c, void* tiles, float* Z, const float* d_M, const float* mu, const float* scales,
+                    uint8_t* Xprep, double* corr) {
+    TmTiles* t = (TmTiles*)tiles;
+    if (t->n_cb == 0) return;
+    tm_zside_apply_kernel<<<(unsigned)(t->n_cb * (TM_DEPTH / 32)), 256, 0, ctx->stream>>>(Z, c->ncols, d_M, mu, scales, Z, Xprep, corr);
+    ctx->n_launch++;
+    SALG_CUDA(cudaGetLastError());
 }
 
 // Z += A^T Y (Z pre-initialised with the centring term), Y given pre-split as tc_gram_prep / tc_prep_kernel<128> write it
