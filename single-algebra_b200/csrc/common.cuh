@@ -330,8 +330,12 @@ void tc_spmm_A_prepped(salg_ctx* ctx, const salg_csr* c, const uint8_t* Xprep, c
 
 // ---- dense.cu -------------------------------------------------------------------------------------
 template <typename T> void panel_gram(salg_ctx* ctx, const T* P, int64_t m, double* d_out /*GRAM_BUF*/);
-template <typename T> void chol_inv(salg_ctx* ctx, const double* d_G, int k, double* d_R, double* d_Rinv, T* d_RinvT, int* d_flag);
-template <typename T> void panel_mul(salg_ctx* ctx, const T* P, int64_t m, const T* d_M /*64x64 row-major*/, T* out);
+// drop: numerically dependent columns get a zero column in R^{-1} (zero column of Q) instead of a floored pivot (dense.cu)
+template <typename T> void chol_inv(salg_ctx* ctx, const double* d_G, int k, double* d_R, double* d_Rinv, T* d_RinvT, int* d_flag,
+                                    bool drop = false);
+// d_amax (optional, zeroed here): receives the bits of max |out| as a float
+template <typename T> void panel_mul(salg_ctx* ctx, const T* P, int64_t m, const T* d_M /*64x64 row-major*/, T* out,
+                                     unsigned* d_amax = nullptr);
 void mat64_mul(salg_ctx* ctx, const double* A, const double* B, double* C);  // C = A*B, 64x64 f64
 void vec64_mat(salg_ctx* ctx, const double* v, const double* M, double* o);  // o = v*M
 void jacobi_svd64(salg_ctx* ctx, const double* d_A, int k, double* d_U, double* d_S, double* d_V, int* d_flag);
@@ -346,7 +350,7 @@ template <typename T> void panel_unpack(salg_ctx* ctx, const T* src, int64_t m, 
 void zside_solve(salg_ctx* ctx, const float* Z, int64_t n, const double* d_Gy, int k, float a_scale, double* d_part,
                  unsigned* d_ticket, float* d_M, float* d_scales, double* d_corr, int* d_flag);
 size_t zside_part_elems();
-bool zside_two_step();
+int zside_mode();
 template <typename T> void cholqr2(salg_ctx* ctx, T* Y, int64_t m_local, int k, bool sharded, double* d_colsum64,
                                    double* d_Rtot, int* d_flag, int passes);
 

@@ -111,22 +111,26 @@ template void panel_gram<double>(salg_ctx*, const double*, int64_t, double*);
 // and inverts it, (2) 8-term triangular products give the panel below and the block row of L^{-1} (forward substitution of
 // the identity, carried along), (3) ONE block-wide rank-8 update of the trailing matrix and of the rows of L^{-1} below.
 // 8 x 3 barriers instead of 64.  The matrix is padded with the identity to 64 x 64, so every block is full.
-// Pivots that are not safely positive are floored (rank-deficient panels: l > rank(A)); flag bit 1 is raised, the
-// caller's second CholeskyQR pass re-orthonormalises.
+// Pivots that are not safely positive (below 1e-13 of the largest diagonal entry; rank-deficient panels: l > rank(A)) raise flag
+// bit 1 and are floored or dropped, see below.
 constexpr int CHOL_THREADS = 512;
 constexpr int CHOL_LD = LP + 1;
 constexpr int CHOL_NB = 8;
-constexpr size_t CHOL_SMEM = (size_t)(2 * LP * CHOL_LD + 2 * CHOL_NB * (CHOL_NB + 1) + 2) * sizeof(double);
+constexpr size_t CHOL_SMEM = (size_t)(2 * LP * CHOL_LD + 2 * CHOL_NB * (CHOL_NB + 1) + 4 + LP) * sizeof(double);
 
 // The factorisation proper, for CHOL_THREADS threads of one CTA: on return (after its last barrier) chol_sm holds L in the
 // lower triangle of A = chol_sm[0 .. 64*65) and L^{-1} in B = chol_sm + 64*65 (both ld CHOL_LD).  G: k x k, leading
-// dimension ldg, global or shared.  Returns whether THIS thread saw a floored pivot (warp 0 only).
-__device__ __forceinline__ bool chol_inv_block(const double* G, int ldg, int k, double* chol_sm) {
+// dimension ldg, global or shared.  Returns THIS thread's flags (warp 0 only): bit 0 a pivot was floored, bit 1 a pivot below
+// warn_rel x the largest diagonal entry.  Not inlined: the fused small-side kernel calls it from three places, and three copies
+// of this unrolled body measured +10 us per launch (instruction-cache misses on a one-CTA latency chain).
+__device__ __noinline__ int chol_inv_block(const double* G, int ldg, int k, double* chol_sm, double warn_rel = 0.0, int drop = 0) {
     double* A = chol_sm;                       // [64][65] lower triangle: trailing matrix, finished columns hold L
     double* B = A + LP * CHOL_LD;              // [64][65] forward-substituted identity, finished rows hold L^{-1}
     double* L8 = B + LP * CHOL_LD;             // [8][9] diagonal block of L
     double* Li8 = L8 + CHOL_NB * (CHOL_NB + 1);   // [8][9] its inverse
     double* s_md = Li8 + CHOL_NB * (CHOL_NB + 1); // [2]
+    int* s_fmask = reinterpret_cast<int*>(s_md + 2);   // dependent columns of the current block
+    double* s_diag = s_md + 4;                         // [64] the matrix's own diagonal (squared column norms of the panel)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c = tid & 63, g = tid >> 6;
 #pragma unroll
@@ -137,6 +141,7 @@ __device__ __forceinline__ bool chol_inv_block(const double* G, int ldg, int k, 
     }
     if (tid < 64) {
         double md = (tid < k) ? G[tid * ldg + tid] : 0.0;
+        s_diag[tid] = (tid < k) ? md : 1.0;
 #pragma unroll
         for (int o = 16; o; o >>= 1) md = fmax(md, __shfl_xor_sync(0xFFFFFFFFu, md, o));
         if ((tid & 31) == 0) s_md[tid >> 5] = md;
@@ -144,30 +149,50 @@ __device__ __forceinline__ bool chol_inv_block(const double* G, int ldg, int k, 
     __syncthreads();
     const double mdiag = fmax(s_md[0], s_md[1]);
     const double floor_piv = (mdiag > 0.0 ? mdiag : 1.0) * 1e-13;
-    bool bad = false;
+    const double warn_piv = (mdiag > 0.0 ? mdiag : 1.0) * warn_rel;
+    int bad = 0;                               // bit 0: a pivot was floored, bit 1: a pivot below warn_rel * (largest diagonal entry)
     for (int j0 = 0; j0 < LP; j0 += CHOL_NB) {
         // ---- (1) diagonal block: lane r (mod 8) holds row r of the block
         if (warp == 0) {
             const int r = lane & 7;
+            int fmask = 0;
             double a[CHOL_NB], di[CHOL_NB];
 #pragma unroll
             for (int cc = 0; cc < CHOL_NB; cc++) a[cc] = A[(j0 + r) * CHOL_LD + j0 + cc];
 #pragma unroll
             for (int j = 0; j < CHOL_NB; j++) {
                 double p = __shfl_sync(0xFFFFFFFFu, a[j], j);
-                if (!(p > floor_piv)) {
-                    p = floor_piv;
-                    bad = true;
+                if (!(p > warn_piv)) bad |= 2;
+                // A pivot that is not safely positive marks a column that (numerically) depends on the ones before it.  Its
+                // sub-diagonal column of L is set to ZERO (no trailing update from it) and
+                //   drop = 0: the pivot is floored: Q = Y R^{-1} gets the residual divided by sqrt(floor) there — amplified
+                //             rounding noise that a following pass re-orthonormalises when it is independent (ill-conditioned
+                //             f32 panels: their true pivots sit at the same 1e-14 as the noise);
+                //   drop = 1: the column is dropped altogether (zero column of L, zero row of L^{-1}: zero column of Q, zero
+                //             row of R).  The LAST pass of a CholeskyQR uses this: what is still dependent after a pass that
+                //             amplified every independent direction to O(1) is an exact dependency (rank(A) < l).
+                // Rounds 1-2 floored the pivot and kept the sub-diagonal column: with several dependent columns the trailing
+                // updates are of the size of the floor itself and grow geometrically (18 dependent columns of a rank-11 f32
+                // sketch: inf / NaN), and never-orthogonal noise columns of Q inflate the singular values of Q^T A.
+                // drop pass: scale-free test against the column's own squared norm (sin^2 of its angle to the span of the
+                // columns before it below 1e-5): the pass before may have left a noise column of any size, and the Gram may
+                // come from the tensor-core pass (fp16 two-term operands: entries good to ~1e-6 of the norms)
+                const bool dep = drop ? !(p > 1e-5 * s_diag[j0 + j]) : !(p > floor_piv);
+                if (dep) {
+                    bad |= 1;
+                    fmask |= 1 << j;
+                    p = drop ? 0.0 : floor_piv;
                 }
-                const double d = rsqrt(p);
+                const double d = (dep && drop) ? 0.0 : rsqrt(p);
                 di[j] = d;
-                a[j] = (r == j) ? p * d : a[j] * d;          // column j of L (rows >= j)
+                a[j] = (r == j) ? p * d : (dep ? 0.0 : a[j] * d);          // column j of L (rows >= j)
 #pragma unroll
                 for (int cc = j + 1; cc < CHOL_NB; cc++) {
                     const double lc = __shfl_sync(0xFFFFFFFFu, a[j], cc);
                     if (r >= cc) a[cc] = fma(-a[j], lc, a[cc]);
                 }
             }
+            if (lane == 0) *s_fmask = fmask;
             if (lane < CHOL_NB) {
 #pragma unroll
                 for (int cc = 0; cc < CHOL_NB; cc++) L8[r * (CHOL_NB + 1) + cc] = (cc <= r) ? a[cc] : 0.0;
@@ -199,7 +224,7 @@ __device__ __forceinline__ bool chol_inv_block(const double* G, int ldg, int k, 
                     double sacc = 0.0;
 #pragma unroll
                     for (int b = 0; b <= aa; b++) sacc = fma(a[b], Li8[aa * (CHOL_NB + 1) + b], sacc);
-                    A[t * CHOL_LD + j0 + aa] = sacc;
+                    A[t * CHOL_LD + j0 + aa] = ((*s_fmask >> aa) & 1) ? 0.0 : sacc;
                 }
             }
         } else if (tid < 128) {
@@ -248,14 +273,14 @@ __device__ __forceinline__ bool chol_inv_block(const double* G, int ldg, int k, 
 template <typename T>
 __global__ void __launch_bounds__(CHOL_THREADS)
 chol_inv_kernel(const double* __restrict__ G, int k, double* __restrict__ R, double* __restrict__ Rinv,
-                T* __restrict__ RinvT, int* __restrict__ flag) {
+                T* __restrict__ RinvT, int* __restrict__ flag, int drop) {
     extern __shared__ double chol_sm[];
     const double* A = chol_sm;
     const double* B = A + LP * CHOL_LD;
     const int tid = threadIdx.x, lane = tid & 31;
     const int c = tid & 63, g = tid >> 6;
-    const bool bad = chol_inv_block(G, LP, k, chol_sm);
-    if (bad && lane == 0) atomicOr(flag, 1);
+    const int bad = chol_inv_block(G, LP, k, chol_sm, 0.0, drop);
+    if ((bad & 1) && lane == 0) atomicOr(flag, 1);
     // outputs (row-major 64 x 64): R[r][i] = L[i][r], Rinv[r][i] = (L^{-1})[i][r]; thread (g, c) writes rows r = g + 8m,
     // column i = c (consecutive threads -> consecutive addresses)
 #pragma unroll
@@ -269,15 +294,15 @@ chol_inv_kernel(const double* __restrict__ G, int k, double* __restrict__ R, dou
 }
 
 template <typename T>
-void chol_inv(salg_ctx* ctx, const double* d_G, int k, double* d_R, double* d_Rinv, T* d_RinvT, int* d_flag) {
+void chol_inv(salg_ctx* ctx, const double* d_G, int k, double* d_R, double* d_Rinv, T* d_RinvT, int* d_flag, bool drop) {
     ProfScope ps(ctx, PROF_CHOL, 0.0);
     set_max_dyn_smem(chol_inv_kernel<T>, (int)((int)CHOL_SMEM));
-    chol_inv_kernel<T><<<1, CHOL_THREADS, CHOL_SMEM, ctx->stream>>>(d_G, k, d_R, d_Rinv, d_RinvT, d_flag);
+    chol_inv_kernel<T><<<1, CHOL_THREADS, CHOL_SMEM, ctx->stream>>>(d_G, k, d_R, d_Rinv, d_RinvT, d_flag, drop ? 1 : 0);
     ctx->n_launch++;
     SALG_CUDA(cudaGetLastError());
 }
-template void chol_inv<float>(salg_ctx*, const double*, int, double*, double*, float*, int*);
-template void chol_inv<double>(salg_ctx*, const double*, int, double*, double*, double*, int*);
+template void chol_inv<float>(salg_ctx*, const double*, int, double*, double*, float*, int*, bool);
+template void chol_inv<double>(salg_ctx*, const double*, int, double*, double*, double*, int*, bool);
 
 // ---- the replicated small side of one power-iteration half step in ONE launch ---------------------------------------------
 // Given the all-reduced raw product Z0 = A_c^T Y (n x 64) the step needs Z2 = an orthonormal basis of span(Z0).  It used to be
@@ -286,11 +311,14 @@ template void chol_inv<double>(salg_ctx*, const double*, int, double*, double*, 
 // row-sharded fit repeats.  Here: CTAs 1..G take the Gram of the RAW panel in f64, GZ = Z0^T Z0 (per-CTA partials in fixed
 // slots, summed in slot order: bit-identical on every rank and from run to run), CTA 0 factors and publishes M with Z2 = Z0 M
 // together with the fp16 pre-split scale for Z2.  Two variants:
-//   two steps (default) CTA 0 factors Gy while the others take the Gram, then G1 = R1^{-T} GZ R1^{-1} (= Z1^T Z1 without
-//                       touching the panel), M = R1^{-1} chol(G1)^{-1}: every Cholesky sees cond kappa^2 (kappa = sigma_1 / sigma_l
-//                       of the sketch), as in the explicit chain.
-//   one step            (SALG_ZSIDE_ONESTEP, experiment) M = chol(GZ)^{-1}: one 28 us Cholesky per half step instead of two, but
-//                       at cond kappa^4 — measured: config 2's raw-count sketch (kappa > 1000) floors a pivot; not the default.
+//   one step   M = chol(GZ)^{-1}: one 28 us Cholesky.  Z0 is already rounded to f32 when R1^{-1} would be applied, so the detour
+//              through Z1 recovers nothing; it only keeps each Cholesky at cond kappa^2 instead of kappa^4 (kappa = sigma_1 /
+//              sigma_l of the sketch).  Measured: config 2's raw-count sketch (kappa > 1000) floors a pivot this way.
+//   two steps  CTA 0 factors Gy (while the others take the Gram), then G1 = R1^{-T} GZ R1^{-1} (= Z1^T Z1 without touching the
+//              panel), M = R1^{-1} chol(G1)^{-1}: every Cholesky sees cond kappa^2, as in the explicit chain.
+//   adaptive   one step; a pivot below 1e-9 of the largest diagonal entry switches this launch and the rest of the fit to two
+//              steps (the decision is taken on bit-identical sums: all ranks agree).  Measured: configs 2 AND 3 both switch in
+//              their first half step, so the default is two steps outright (SALG_ZSIDE_MODE = 1; 0 adaptive, 2 one step).
 // Columns of Z2 have unit norm unless a pivot was floored; then the bound for the pre-split comes from diag(M^T GZ M).
 // A second launch (tm.cu: tm_zside_apply_kernel) applies M, takes mu^T Z2 and writes the pre-split operand of the next A X.
 constexpr int ZS_MAX_G = 64;
@@ -329,7 +357,7 @@ __device__ __forceinline__ void zs_mat64(const double* X, const double* Y, doubl
 }
 
 __global__ void __launch_bounds__(CHOL_THREADS)
-zside_solve_kernel(const float* __restrict__ Z, int64_t n, const double* __restrict__ Gy, int k, float a_scale, int two_step,
+zside_solve_kernel(const float* __restrict__ Z, int64_t n, const double* __restrict__ Gy, int k, float a_scale, int mode,
                    double* __restrict__ part /* [gridDim.x - 1][4096] */, unsigned* __restrict__ ticket,
                    float* __restrict__ M_out, float* __restrict__ scales, double* __restrict__ corr, int* __restrict__ flag) {
     extern __shared__ double chol_sm[];
@@ -393,15 +421,20 @@ zside_solve_kernel(const float* __restrict__ Z, int64_t n, const double* __restr
     double* T = S + LP * CHOL_LD;
     double* U = T + LP * CHOL_LD;
     const int c = tid & 63, g = tid >> 6;
-    bool bad = false;
-    if (two_step) {
-        bad = chol_inv_block(Gy, LP, k, chol_sm);                              // (while the other CTAs take the Gram)
+    // mode 0: adaptive — try the one-step factorisation of GZ; a pivot below 1e-9 of the largest diagonal entry
+    // (cond(GZ) beyond ~1e9, i.e. kappa beyond ~180) falls back to the two-step chain in this launch and makes the later
+    // launches of the fit go there directly (sticky word ticket[1], reset by the host per fit).  1: two steps, 2: one step.
+    const bool sticky = mode == 1 || (mode == 0 && __ldcg(ticket + 1) != 0u);
+    int bad = 0;
+    auto factor_gy = [&]() {
+        bad |= chol_inv_block(Gy, LP, k, chol_sm) & 1;
 #pragma unroll
         for (int m = 0; m < 8; m++) {
             const int r = g + 8 * m;
             RiS[r * CHOL_LD + c] = (r <= c) ? B[c * CHOL_LD + r] : 0.0;        // R1^{-1}[r][c] = (L^{-1})[c][r]
         }
-    }
+    };
+    if (sticky) factor_gy();                                                   // (while the other CTAs take the Gram)
     if (tid < LP) corr[tid] = 0.0;
     if (tid == 0) {
         while (atomicAdd(ticket, 0u) < (unsigned)G) __nanosleep(32);
@@ -432,12 +465,31 @@ zside_solve_kernel(const float* __restrict__ Z, int64_t n, const double* __restr
     }
     if (tid == 0) *ticket = 0u;                                               // ready for the next launch on this stream
     __syncthreads();
-    if (two_step) {
+    bool two = sticky;
+    if (!two) {
+        const int f = chol_inv_block(S, CHOL_LD, k, chol_sm, mode == 2 ? 0.0 : 1e-9);
+        const int weak = __syncthreads_or(f != 0 ? 1 : 0);
+        if (weak && mode == 0) {
+            if (tid == 0) ticket[1] = 1u;
+            __syncthreads();
+            factor_gy();
+            two = true;
+        } else {
+            bad |= f & 1;
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                const int r = g + 8 * m;
+                T[r * CHOL_LD + c] = (r <= c) ? B[c * CHOL_LD + r] : 0.0;      // M = R^{-1}
+            }
+        }
+    }
+    if (two) {
+        __syncthreads();
         zs_mat64<false>(S, RiS, T);                                           // T = GZ R1^{-1}
         __syncthreads();
         zs_mat64<true>(RiS, T, U);                                            // U = R1^{-T} GZ R1^{-1} = Z1^T Z1
         __syncthreads();
-        bad |= chol_inv_block(U, CHOL_LD, k, chol_sm);
+        bad |= chol_inv_block(U, CHOL_LD, k, chol_sm) & 1;
 #pragma unroll
         for (int m = 0; m < 8; m++) {
             const int r = g + 8 * m;
@@ -445,38 +497,39 @@ zside_solve_kernel(const float* __restrict__ Z, int64_t n, const double* __restr
         }
         __syncthreads();
         zs_mat64<false>(RiS, U, T);                                           // M = R1^{-1} R2^{-1}
-    } else {
-        bad = chol_inv_block(S, CHOL_LD, k, chol_sm);
-#pragma unroll
-        for (int m = 0; m < 8; m++) {
-            const int r = g + 8 * m;
-            T[r * CHOL_LD + c] = (r <= c) ? B[c * CHOL_LD + r] : 0.0;          // M = R^{-1}
-        }
     }
-    const int any_bad = __syncthreads_or(bad ? 1 : 0);
+    const int any_bad = __syncthreads_or(bad != 0 ? 1 : 0);
 #pragma unroll
     for (int m = 0; m < 8; m++) {
         const int r = g + 8 * m;
         M_out[r * LP + c] = (float)T[r * CHOL_LD + c];
     }
     if (any_bad) {
+        // floored pivots: columns of Z2 are no longer unit vectors and M^T GZ M cancels too heavily to bound them, so the
+        // largest |entry| of Z0 M is taken from the panel itself (one CTA, rare: rank-deficient sketches)
         if (tid == 0) atomicOr(flag, 1);
-        zs_mat64<false>(S, T, RiS);                                           // GZ M
         __syncthreads();
-        if (tid < LP) {
-            double d = 0.0;
-            for (int i = 0; i < LP; i++) d = fma(T[i * CHOL_LD + tid], RiS[i * CHOL_LD + tid], d);   // ||column tid of Z2||^2
-            d = (tid < k && d > 0.0) ? d : 0.0;
+        double mx = 0.0;
+        for (int64_t r = g; r < n; r += 8) {
+            double acc = 0.0;
+            for (int kk = 0; kk < LP; kk++) acc = fma((double)Z[r * LP + kk], T[kk * CHOL_LD + c], acc);
+            mx = fmax(mx, fabs(acc));
+        }
 #pragma unroll
-            for (int o = 16; o; o >>= 1) d = fmax(d, __shfl_xor_sync(0xFFFFFFFFu, d, o));
-            if (lane == 0) U[tid >> 5] = d;
+        for (int o = 16; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+        if (lane == 0) RiS[tid >> 5] = mx;
+        __syncthreads();
+        if (tid == 0) {
+            double m2 = 0.0;
+            for (int w = 0; w < CHOL_THREADS / 32; w++) m2 = fmax(m2, RiS[w]);
+            U[0] = m2;
         }
         __syncthreads();
     }
     if (tid == 0) {
-        const double d = any_bad ? fmax(U[0], U[1]) : 1.0;
-        // |z| <= its column's norm (1 up to rounding unless a pivot was floored); 1/16 of slack for the f32 arithmetic
-        const float bound = (isfinite(d) && d > 0.0) ? (float)(sqrt(d) * 1.0625) : 1.0625f;
+        // |z| <= its column's norm = 1 up to rounding (no floored pivot), else the measured maximum; 1/16 of slack for the f32 apply
+        const double d = any_bad ? U[0] : 1.0;
+        const float bound = (isfinite(d) && d > 0.0) ? (float)(d * 1.0625) : 1.0625f;
         const float sc = tc_pow2_scale_dev(bound);
         scales[0] = sc;
         scales[1] = 1.f / (sc * a_scale);
@@ -486,17 +539,17 @@ zside_solve_kernel(const float* __restrict__ Z, int64_t n, const double* __restr
 void zside_solve(salg_ctx* ctx, const float* Z, int64_t n, const double* d_Gy, int k, float a_scale, double* d_part,
                  unsigned* d_ticket, float* d_M, float* d_scales, double* d_corr, int* d_flag) {
     ProfScope ps(ctx, PROF_CHOL, 0.0);
-    const int two_step = zside_two_step() ? 1 : 0;
     const int64_t tiles = ceil_div(n, 64);
     const int G = (int)std::max<int64_t>(1, std::min<int64_t>(ZS_MAX_G, ceil_div(tiles, 2)));
     set_max_dyn_smem(zside_solve_kernel, (int)ZS_SMEM);
-    zside_solve_kernel<<<1 + G, CHOL_THREADS, ZS_SMEM, ctx->stream>>>(Z, n, d_Gy, k, a_scale, two_step, d_part, d_ticket, d_M,
+    zside_solve_kernel<<<1 + G, CHOL_THREADS, ZS_SMEM, ctx->stream>>>(Z, n, d_Gy, k, a_scale, zside_mode(), d_part, d_ticket, d_M,
                                                                       d_scales, d_corr, d_flag);
     ctx->n_launch++;
     SALG_CUDA(cudaGetLastError());
 }
-bool zside_two_step() {
-    static const bool v = getenv("SALG_ZSIDE_ONESTEP") == nullptr;
+// SALG_ZSIDE_MODE: 1 two steps (default), 0 adaptive, 2 one step always (experiments)
+int zside_mode() {
+    static const int v = getenv("SALG_ZSIDE_MODE") ? atoi(getenv("SALG_ZSIDE_MODE")) : 1;
     return v;
 }
 size_t zside_part_elems() { return (size_t)ZS_MAX_G * LP * LP; }
@@ -504,7 +557,7 @@ size_t zside_part_elems() { return (size_t)ZS_MAX_G * LP * LP; }
 // ---- out = P * M (M 64 x 64 row-major, T); in place allowed ------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256)
-panel_mul_kernel(const T* P, int64_t m, const T* __restrict__ M, T* out) {
+panel_mul_kernel(const T* P, int64_t m, const T* __restrict__ M, T* out, unsigned* __restrict__ amax_out) {
     constexpr int TR = 64;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     T (*Ms)[LP] = reinterpret_cast<T (*)[LP]>(dyn_smem);
@@ -513,6 +566,7 @@ panel_mul_kernel(const T* P, int64_t m, const T* __restrict__ M, T* out) {
     const int ty = tid >> 4, tx = tid & 15;   // rows 4ty..4ty+3, cols 4tx..4tx+3
     for (int i = tid; i < LP * LP; i += 256) Ms[i >> 6][i & 63] = M[i];
     const int64_t n_tiles = (m + TR - 1) / TR;
+    float amax = 0.f;
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const int64_t r0 = t * TR;
         __syncthreads();
@@ -551,26 +605,35 @@ panel_mul_kernel(const T* P, int64_t m, const T* __restrict__ M, T* out) {
             int64_t r = r0 + 4 * ty + x;
             if (r < m) {
 #pragma unroll
-                for (int y = 0; y < 4; y++) out[r * LP + 4 * tx + y] = acc[x][y];
+                for (int y = 0; y < 4; y++) {
+                    out[r * LP + 4 * tx + y] = acc[x][y];
+                    amax = fmaxf(amax, fabsf((float)acc[x][y]));
+                }
             }
         }
+    }
+    if (amax_out) {                      // bits of max |out| (zeroed by the caller)
+#pragma unroll
+        for (int o = 16; o; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xFFFFFFFFu, amax, o));
+        if ((tid & 31) == 0 && amax > 0.f) atomicMax(amax_out, __float_as_uint(amax));
     }
 }
 
 template <typename T>
-void panel_mul(salg_ctx* ctx, const T* P, int64_t m, const T* d_M, T* out) {
+void panel_mul(salg_ctx* ctx, const T* P, int64_t m, const T* d_M, T* out, unsigned* d_amax) {
+    if (d_amax) SALG_CUDA(cudaMemsetAsync(d_amax, 0, 4, ctx->stream));
     if (m == 0) return;
     ProfScope ps(ctx, PROF_PANELMUL, 2.0 * (double)m * 60 * sizeof(T));
     int64_t want = ceil_div(m, 64);
     int64_t cap = (int64_t)ctx->sm_count * 4;
     constexpr int kSmem = (int)sizeof(T) * (LP * LP + LP * (64 + 4));
     set_max_dyn_smem(panel_mul_kernel<T>, (int)(kSmem));
-    panel_mul_kernel<T><<<(unsigned)(want < cap ? want : cap), 256, kSmem, ctx->stream>>>(P, m, d_M, out);
+    panel_mul_kernel<T><<<(unsigned)(want < cap ? want : cap), 256, kSmem, ctx->stream>>>(P, m, d_M, out, d_amax);
     ctx->n_launch++;
     SALG_CUDA(cudaGetLastError());
 }
-template void panel_mul<float>(salg_ctx*, const float*, int64_t, const float*, float*);
-template void panel_mul<double>(salg_ctx*, const double*, int64_t, const double*, double*);
+template void panel_mul<float>(salg_ctx*, const float*, int64_t, const float*, float*, unsigned*);
+template void panel_mul<double>(salg_ctx*, const double*, int64_t, const double*, double*, unsigned*);
 
 // ---- 64 x 64 f64 helpers ------------------------------------------------------------------------------------
 __global__ void mat64_mul_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C) {
@@ -697,10 +760,21 @@ __device__ __forceinline__ int jacobi_sweeps(F (*W)[LP + 1], F (*Vt)[LP + 1], in
                 gamma += __shfl_xor_sync(0xFFFFFFFFu, gamma, o);
             }
             // |gamma| > tol sqrt(alpha beta)  <=>  gamma^2 > tol^2 alpha beta  (no square root on the chain)
-            if (active && gamma * gamma > tol * tol * alpha * beta && gamma != F(0)) {
+            // (columns whose squared norm is in or near the subnormal range are left to the f64 phase / are zero: the products
+            // alpha * beta and the reciprocal of 2 gamma would under- / overflow: inf * 0 = NaN in the rotation parameters)
+            const F tiny = sizeof(F) == 4 ? F(1e-30) : F(1e-280);
+            if (active && alpha > tiny && beta > tiny && gamma * gamma > tol * tol * alpha * beta && gamma != F(0)) {
                 F zeta = (beta - alpha) * JacMath<F>::rcp(F(2) * gamma);
-                F h2 = fma(zeta, zeta, F(1));
-                F w = h2 * JacMath<F>::rsq(h2);                                   // sqrt(1 + zeta^2)
+                // sqrt(1 + zeta^2); beyond `big` it IS |zeta| to working precision, and zeta^2 would overflow (columns whose
+                // norms differ by 1e17 and more, e.g. the 1e-14 rows a rank-deficient f64 sketch leaves in R beside sigma ~ 500:
+                // inf * rsqrt(inf) = NaN used to poison the whole factor)
+                const F az = fabs(zeta);
+                const F big = sizeof(F) == 4 ? F(1e8) : F(1e150);
+                F w = az;
+                if (!(az > big)) {
+                    const F h2 = fma(zeta, zeta, F(1));
+                    w = h2 * JacMath<F>::rsq(h2);
+                }
                 F t = (zeta >= F(0) ? F(1) : F(-1)) * JacMath<F>::rcp(fabs(zeta) + w);
                 F c = JacMath<F>::rsq(fma(t, t, F(1))), sn = c * t;
 #pragma unroll
@@ -807,11 +881,14 @@ jacobi_svd64_kernel(const double* __restrict__ A, int k, double* __restrict__ U,
     }
     __syncthreads();
     if (tid < LP) {
-        // rank by descending sigma (stable on index)
+        // rank by descending sigma (stable on index); a non-finite value sorts last, so `order` is a permutation whatever
+        // the input held (a NaN used to leave entries of `order` unset: out-of-range reads below)
         int rank = 0;
-        double me = sig[tid];
+        const double raw = sig[tid];
+        const double me = isfinite(raw) ? raw : -2.0;
         for (int j = 0; j < LP; j++) {
-            double o = sig[j];
+            const double oraw = sig[j];
+            const double o = isfinite(oraw) ? oraw : -2.0;
             rank += (o > me) || (o == me && j < tid);
         }
         order[rank] = tid;
@@ -1028,7 +1105,7 @@ void cholqr2(salg_ctx* ctx, T* Y, int64_t m_local, int k, bool sharded, double* 
         if (sharded) allreduce_f64(ctx, G.get(), GRAM_BUF);
         double* R = pass == 0 ? R1.get() : R2.get();
         double* Ri = pass == 0 ? Ri1.get() : Ri2.get();
-        chol_inv<T>(ctx, G.get(), k, R, Ri, RiT.get(), d_flag);
+        chol_inv<T>(ctx, G.get(), k, R, Ri, RiT.get(), d_flag, passes > 1 && pass == passes - 1);   // (last of two: drop what is still dependent)
         panel_mul<T>(ctx, Y, m_local, RiT.get(), Y);
         if (d_colsum64) {
             if (pass == 0) vec64_mat(ctx, G.get() + LP * LP, Ri, passes == 1 ? d_colsum64 : cs.get());

@@ -299,6 +299,11 @@ static salg_pca* pca_fit(salg_ctx* ctx, const salg_csr* x, const salg_pca_params
         if (center)
             for (int64_t c = 0; c < ncols; c++) P->mean_full[c] = h_sum[c] / n_d;
         P->total_var = tv;
+        // squared Frobenius norm of the operator the SVD sees (centred or not): every correct factorisation has
+        // sum sigma_i^2 below it; checked at the end (a mis-normalised basis from a rank-deficient sketch does not)
+        double raw2 = 0.0;
+        for (int64_t i = 0; i < n_eff; i++) raw2 += h_sq[mask ? kept[i] : i];
+        const double fro2 = center ? tv * (n_d - 1.0) : raw2;
 
         // ---- operator: the (column-compacted) matrix
         const salg_csr* op = x;
@@ -409,8 +414,8 @@ static salg_pca* pca_fit(salg_ctx* ctx, const salg_csr* x, const salg_pca_params
                     zfused = tc_zside_supported(ctx, op) && !getenv("SALG_NO_ZSIDE");
                     if (zfused) {
                         zpart.alloc(zside_part_elems(), st);
-                        zticket.alloc(1, st);
-                        SALG_CUDA(cudaMemsetAsync(zticket.get(), 0, 4, st));
+                        zticket.alloc(2, st);                          // {arrival counter, sticky two-step word}
+                        SALG_CUDA(cudaMemsetAsync(zticket.get(), 0, 8, st));
                         zM.alloc(LP * LP, st);
                         zscales.alloc(2, st);
                         zXprep.alloc(tc_xprep_bytes(ctx, op) + 16, st);
@@ -436,7 +441,7 @@ static salg_pca* pca_fit(salg_ctx* ctx, const salg_csr* x, const salg_pca_params
                         // every rank centres its partial with ITS OWN column sums: sum_r (A_r^T Y_r - mu cs_r^T) is the
                         // centred product, so the Gram / column sums and the partial panel share one NCCL launch
                         tc_gram_prep(ctx, op, Y.get(), yamax.get(), Yprep.get(), yscales.get(), Gy.get(),
-                                     zfused && !zside_two_step());       // (the one-step small side needs no Gram of Y)
+                                     zfused && zside_mode() == 2);       // (the pure one-step small side needs no Gram of Y)
                         tc_spmm_At_prepped(ctx, op, Yprep.get(), yscales.get(), Z.get(), d_mu,
                                            center ? Gy.get() + LP * LP : nullptr);
                         allreduce_gram_and_panel(ctx, Gy.get(), GRAM_BUF, Z.get(), (size_t)n_eff * LP);
@@ -481,13 +486,16 @@ static salg_pca* pca_fit(salg_ctx* ctx, const salg_csr* x, const salg_pca_params
                     tc_gram_prep(ctx, op, Y.get(), yamax.get(), Yprep.get(), yscales.get(), Gy.get());
                     allreduce_f64(ctx, Gy.get(), GRAM_BUF);
                     chol_inv<T>(ctx, Gy.get(), l, nullptr, nullptr, RiT.get(), d_flag.get());
-                    panel_mul<T>(ctx, Y.get(), m_loc, RiT.get(), Y.get());
-                    tc_set_amax(ctx, yamax.get(), 1.0625f);      // columns of Q1 have norm 1 +- (Gram rounding): |q| <= 1.06
+                    // |max| of Q1 rides on the product: columns of Q1 have unit norm only while no pivot was floored (a
+                    // rank-deficient sketch leaves amplified rounding noise of any size in the dependent columns; assuming
+                    // |q| <= 1.06 there overflowed the fp16 split: non-finite singular values)
+                    panel_mul<T>(ctx, Y.get(), m_loc, RiT.get(), Y.get(), yamax.get());
+                    // (per-rank |max| and scale, as after every A X: each rank un-scales its own partial products)
                     tc_gram_prep(ctx, op, Y.get(), yamax.get(), Yprep.get(), yscales.get(), Gy.get());
                     tc_spmm_At_prepped(ctx, op, Yprep.get(), yscales.get(), Z.get(), d_mu,
                                        center ? Gy.get() + LP * LP : nullptr);       // local column sums (see above)
                     allreduce_gram_and_panel(ctx, Gy.get(), GRAM_BUF, Z.get(), (size_t)n_eff * LP);
-                    chol_inv<T>(ctx, Gy.get(), l, nullptr, nullptr, RiT.get(), d_flag.get());
+                    chol_inv<T>(ctx, Gy.get(), l, nullptr, nullptr, RiT.get(), d_flag.get(), true);   // second pass: drop exact dependencies
                     panel_mul<T>(ctx, Z.get(), n_eff, RiT.get(), Z.get());
                     final_done = true;
                 }
@@ -588,6 +596,14 @@ static salg_pca* pca_fit(salg_ctx* ctx, const salg_csr* x, const salg_pca_params
                          prm->svd_method == SALG_SVD_RANDOM ? "Randomized SVD computation failed: non-finite singular value"
                                                             : "SVD computation failed: non-finite singular value");
             P->explained_variance[i] = s * s / (n_d - 1.0);   // pca/sparse/mod.rs:210-216
+        }
+        if (prm->svd_method == SALG_SVD_RANDOM) {
+            double s2 = 0.0;
+            for (double sv : P->singular_values) s2 += sv * sv;
+            // (f32 statistics and products: 1e-3 of slack; the failure this guards against overshoots by orders of magnitude)
+            SALG_REQUIRE(s2 <= fro2 * (1.0 + 1e-3) + 1e-9 * raw2 + 1e-300, SALG_ERR_NUMERIC,
+                         "Randomized SVD computation failed: the projected factor exceeds the operator's Frobenius norm "
+                         "(rank-deficient sketch: fewer independent directions than n_components + n_oversamples)");
         }
         if (!center) {   // pca/sparse/mod.rs:218-223: without centring the total is the sum over components
             double t = 0.0;
