@@ -369,8 +369,8 @@ def run_ours(args, wl):
                for k, v in merged.items()}
     # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the two product kernels from ONE
     # `ncu --set full` capture each, on this workload at 1 GPU (profiles/, see TRAFFIC_SRC)
-    TRAFFIC_SRC = "profiles/r02_ncu_full_top_kernels.csv"
-    ncu_traffic = {("cfg3", "spmm"): 1.094799e9 + 0.236912e9, ("cfg3", "spmm_t"): 1.239400e9 + 0.009086e9}
+    TRAFFIC_SRC = "profiles/r02c_ncu_full_top_kernels.csv"
+    ncu_traffic = {("cfg3", "spmm"): 1.094885e9 + 0.236818e9, ("cfg3", "spmm_t"): 1.238378e9 + 0.006522e9}
     dom = max((k for k in ("spmm", "spmm_t") if k in prof), key=lambda k: prof[k][0], default=None)
     roofline = None
     if dom:
@@ -466,6 +466,9 @@ def run_ours(args, wl):
                         "tile_format": "masked fits rebuild the tile format every fit (inside value and e2e); unmasked "
                                        "operators cache it on the handle: after warm-up `value` excludes that one-time "
                                        "build, e2e (fresh upload per step) includes it",
+                        "small_side": "one launch per half step for Cholesky(Y^T Y) / Gram(Z) / Cholesky -> M and one for Z M + "
+                                      "centring term + fp16 pre-split (90 launches per fit, round 1: 140); the A X time of an "
+                                      "inner iteration no longer contains the pre-split of its panel",
                         "host_cpus_bound_to_gpu_numa_node_rank0": numa_cpus,
                         "step": ("restore raw counts (D2D) + fused preprocess + fit_transform" if wl.get("preprocess")
                                  else "fit_transform")},

@@ -149,7 +149,6 @@ __device__ __noinline__ int chol_inv_block(const double* G, int ldg, int k, doub
     __syncthreads();
     const double mdiag = fmax(s_md[0], s_md[1]);
     const double floor_piv = (mdiag > 0.0 ? mdiag : 1.0) * 1e-13;
-    const double warn_piv = (mdiag > 0.0 ? mdiag : 1.0) * warn_rel;
     int bad = 0;                               // bit 0: a pivot was floored, bit 1: a pivot below warn_rel * (largest diagonal entry)
     for (int j0 = 0; j0 < LP; j0 += CHOL_NB) {
         // ---- (1) diagonal block: lane r (mod 8) holds row r of the block
@@ -162,7 +161,7 @@ __device__ __noinline__ int chol_inv_block(const double* G, int ldg, int k, doub
 #pragma unroll
             for (int j = 0; j < CHOL_NB; j++) {
                 double p = __shfl_sync(0xFFFFFFFFu, a[j], j);
-                if (!(p > warn_piv)) bad |= 2;
+                if (warn_rel > 0.0 && !(p > warn_rel * s_diag[j0 + j])) bad |= 2;   // (scale-free: sin^2 of the column's angle to the span before it)
                 // A pivot that is not safely positive marks a column that (numerically) depends on the ones before it.  Its
                 // sub-diagonal column of L is set to ZERO (no trailing update from it) and
                 //   drop = 0: the pivot is floored: Q = Y R^{-1} gets the residual divided by sqrt(floor) there — amplified
@@ -421,10 +420,11 @@ zside_solve_kernel(const float* __restrict__ Z, int64_t n, const double* __restr
     double* T = S + LP * CHOL_LD;
     double* U = T + LP * CHOL_LD;
     const int c = tid & 63, g = tid >> 6;
-    // mode 0: adaptive — try the one-step factorisation of GZ; a pivot below 1e-9 of the largest diagonal entry
-    // (cond(GZ) beyond ~1e9, i.e. kappa beyond ~180) falls back to the two-step chain in this launch and makes the later
-    // launches of the fit go there directly (sticky word ticket[1], reset by the host per fit).  1: two steps, 2: one step.
-    const bool sticky = mode == 1 || (mode == 0 && __ldcg(ticket + 1) != 0u);
+    // mode 0: adaptive — the first half step of a fit (random mixtures: cond kappa^4) takes two steps; later ones try the
+    // one-step factorisation of GZ and fall back, in the same launch, when a column stands at less than 1e-3 rad to the span
+    // of the columns before it (pivot below 1e-6 of its own squared norm).  ticket[1] = a half step was taken (host: 0 per fit).
+    // 1: two steps always, 2: one step always.
+    const bool sticky = mode == 1 || (mode == 0 && __ldcg(ticket + 1) == 0u);   // adaptive: the FIRST half step of a fit goes two steps outright
     int bad = 0;
     auto factor_gy = [&]() {
         bad |= chol_inv_block(Gy, LP, k, chol_sm) & 1;
@@ -463,14 +463,16 @@ zside_solve_kernel(const float* __restrict__ Z, int64_t n, const double* __restr
 #pragma unroll
         for (int m = 0; m < 8; m++) S[(g + 8 * m) * CHOL_LD + c] = sacc[m];
     }
-    if (tid == 0) *ticket = 0u;                                               // ready for the next launch on this stream
+    if (tid == 0) {
+        *ticket = 0u;                                                         // ready for the next launch on this stream
+        ticket[1] = 1u;                                                       // (a half step of this fit has been taken)
+    }
     __syncthreads();
     bool two = sticky;
     if (!two) {
-        const int f = chol_inv_block(S, CHOL_LD, k, chol_sm, mode == 2 ? 0.0 : 1e-9);
+        const int f = chol_inv_block(S, CHOL_LD, k, chol_sm, mode == 2 ? 0.0 : 1e-6);
         const int weak = __syncthreads_or(f != 0 ? 1 : 0);
         if (weak && mode == 0) {
-            if (tid == 0) ticket[1] = 1u;
             __syncthreads();
             factor_gy();
             two = true;

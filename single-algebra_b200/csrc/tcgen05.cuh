@@ -13,7 +13,10 @@ constexpr uint32_t TC_SPIN_LIMIT = TC_SPIN_LIMIT_;     // polls before a waiting
 // suspend-time hint of mbarrier.try_wait: a waiting thread sleeps in hardware until the phase completes (or this many
 // ns pass) instead of re-issuing the poll; with the default hint the ~25 waiting lanes of a CTA were measured to take
 // most of the issue slots of the SM (ncu: 62 % issue utilisation, three quarters of it poll loops)
-constexpr uint32_t TC_WAIT_HINT_NS = 200000u;
+#ifndef TC_WAIT_HINT_NS_
+#define TC_WAIT_HINT_NS_ 200000u
+#endif
+constexpr uint32_t TC_WAIT_HINT_NS = TC_WAIT_HINT_NS_;
 #ifndef TC_FAST_WAITS_
 #define TC_FAST_WAITS_ 0
 #endif
