@@ -8,8 +8,7 @@ for rows in (125000, 1000000):
     r = salg.op_tall_gram(ctx=ctx, device_rows=rows, k=60, iters=50)
     print("rows", rows, "ms", r if not isinstance(r, tuple) else r[-1], flush=True)
 '''
-for lib in ("", "scratch/libsalg_h20000.so", "scratch/libsalg_h1000.so"):
-    e = dict(os.environ)
-    if lib: e["SALG_LIB_PATH"] = lib
-    print("=== lib", lib or "default (hint 200 us)", flush=True)
+for dbg in ("0", "7", "39"):
+    e = dict(os.environ); e["SALG_GP_DBG"] = dbg
+    print("=== SALG_GP_DBG", dbg, flush=True)
     subprocess.run([sys.executable, "-c", CODE], env=e)
