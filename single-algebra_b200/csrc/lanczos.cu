@@ -328,7 +328,8 @@ int lanczos_svd(salg_ctx* ctx, const salg_csr* op, int k, int max_steps, uint64_
     };
     auto norm_store = [&](const T* w, int64_t len, bool sharded, const double* ref, T* dst, double* out_coef) {
         SALG_CUDA(cudaMemsetAsync(sq.get(), 0, 8, st));
-        if (len) { sqnorm_kernel<T><<<(unsigned)std::min<int64_t>(ceil_div(len, 256), 1024), 256, 0, st>>>(w, len, sq.get()); ctx->n_launch++; }
+        // (one f64 atomic per CTA on ONE address: same-address atomics serialise in L2 at ~25 clk each, so the grid stays at one CTA per SM)
+        if (len) { sqnorm_kernel<T><<<(unsigned)std::min<int64_t>(ceil_div(len, 256 * 8), ctx->sm_count), 256, 0, st>>>(w, len, sq.get()); ctx->n_launch++; }
         if (sharded) allreduce_f64(ctx, sq.get(), 1);
         normalize_store_kernel<T><<<(unsigned)ceil_div(len > 0 ? len : 1, 256), 256, 0, st>>>(
             w, len, sq.get(), ref, 100.0 * eps_t, dst, out_coef);

@@ -1,3 +1,6 @@
+"""Probe (GPU): average time of the fused Gram + pre-split pass (tc_gram_prep_kernel) for a 125k-row (8-GPU shard) and a 1M-row panel
+under its timing switches SALG_GP_DBG (1 no store, 2 no MMA, 4 no load, 32 no Gram; results are wrong with a bit set).
+profiles/r02c_summary.md section 3."""
 import os, sys, subprocess
 CODE = r'''
 import sys, numpy as np

@@ -1,3 +1,5 @@
+"""Probe (GPU): randomized fits of an exactly rank-deficient matrix (3000 cells = copies of 12 profiles, sketch l = 30) under the
+schedule switches of the library; prints the leading singular values against the dense SVD.  See DESIGN.md 4b."""
 import os, sys, subprocess
 CODE = r'''
 import os, numpy as np, scipy.sparse as sp, sys
@@ -22,7 +24,7 @@ for q in (0, 2):
     except Exception as e:
         print("q", q, "FAILED", e, flush=True)
 '''
-for env in ({"DBG_F64": "1", "SALG_JACOBI_DBG": "1"}, {}):
+for env in ({}, {"SALG_NO_ZSIDE": "1"}, {"SALG_NO_FUSED_FINAL": "1"}, {"DBG_IMPL": "chunk"}, {"DBG_F64": "1"}):
     e = dict(os.environ); e.update(env)
     print("=== env", env, flush=True)
     subprocess.run([sys.executable, "-c", CODE], env=e)
