@@ -273,8 +273,16 @@ int salg_pca_total_var(const salg_pca* pca, double* out);
 /* Samples (rows over ALL ranks) the model was fitted on: the n of explained_variance = s^2 / (n - 1)
  * (pca/sparse/mod.rs:210-216) and of the noise-variance estimate the reference prints (:225-238). */
 int salg_pca_n_samples(const salg_pca* pca, int64_t* out);
-/* bit 1: a Cholesky pivot was floored (rank-deficient panel); bit 2: Jacobi sweep limit reached;
- * bit 4: Lanczos returned before every requested triplet met the acceptance bound */
+/* bit 1: a sketch column was numerically dependent on the ones before it (rank-deficient panel: rank(A) below
+ *        n_components + n_oversamples, or an ill-conditioned f32 panel): its Cholesky pivot was floored and, when it was
+ *        still dependent in the last CholeskyQR pass, the column was dropped — the triplets past the numerical rank then
+ *        come back as zero singular values with zero component rows (the reference's Householder QR completes the basis
+ *        with arbitrary orthonormal vectors instead);
+ * bit 2: Jacobi sweep limit reached;
+ * bit 4: Lanczos returned before every requested triplet met the acceptance bound.
+ * A randomized fit whose singular values exceed the operator's Frobenius norm (sum s_i^2 > ||A_c||_F^2, known from the
+ * statistics pass) returns SALG_ERR_NUMERIC "Randomized SVD computation failed: ..." instead of a model (rank-deficient
+ * sketch with n_power_iterations = 0). */
 int salg_pca_numeric_flags(const salg_pca* pca, int* out);
 /* SparsePCA::transform (pca/sparse/mod.rs:255-285) / MaskedSparsePCA::transform
  * (pca/sparse_masked/mod.rs:438-546): scores nrows(x) x d row-major into `scores` (host). */
