@@ -76,8 +76,9 @@ def test_small_svd_matches_lapack(salg, ctx, k):
 
 
 def test_tc_products_match_chunk_kernels_and_f64(salg, ctx):
-    """tcgen05 tile-densified products vs the CUDA-core kernels vs f64: exact-bf16 operator (raw counts, one
-    operator term) and a general float operator (three terms), ragged shapes, both products."""
+    """tcgen05 products vs the CUDA-core kernels vs f64: exact-fp16 operator (raw counts, one operator term) and a general
+    float operator (two fp16 terms; the dense panel is always two fp16 terms = 22 significant bits, tc.cu:15-18), ragged
+    shapes, both products."""
     rng = np.random.default_rng(5)
     for make_general in (False, True):
         A = planted_counts(1000 + 37, 300 + 11, seed=31, dtype=np.float32)      # not multiples of 128 / 64
@@ -96,7 +97,7 @@ def test_tc_products_match_chunk_kernels_and_f64(salg, ctx):
             scale = np.abs(ref).max()
             assert np.abs(got_tc - ref).max() <= 2e-5 * scale, (make_general, transposed)
             assert np.abs(got_ch - ref).max() <= 2e-5 * scale
-            # the split-bf16 tensor-core product is as accurate as the f32 FMA chain
+            # the two-term fp16 tensor-core product (exact products, f32 accumulation) is as accurate as the f32 FMA chain
             assert np.abs(got_tc - ref).max() <= 4 * np.abs(got_ch - ref).max() + 1e-6 * scale
 
 
