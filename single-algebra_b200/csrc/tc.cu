@@ -962,10 +962,16 @@ tc_ax_kernel(const uint2* __restrict__ entries, const int64_t* __restrict__ tile
 // so the f32 accumulation never spans more than GP_DRAIN * 128 rows.  Replaces four passes over the panel (Gram, R^{-1}
 // apply, |max|, pre-split) of the explicit CholeskyQR step: the power iteration applies R^{-1} to the SMALL side instead
 // (A^T (Y R^{-1}) = (A^T Y) R^{-1}).  Column sums 1^T Y ride along in f64.
+#ifndef GP_STAGES_
+#define GP_STAGES_ 3
+#endif
+#ifndef GP_OPS_
+#define GP_OPS_ 2
+#endif
 struct GpSmem {
-    static constexpr int STAGES = 3;
+    static constexpr int STAGES = GP_STAGES_;
     static constexpr int STAGE_BYTES = TC_RB * LP * 4;        // 32 KB of f32 rows
-    static constexpr int OPS = 2;
+    static constexpr int OPS = GP_OPS_;
     static constexpr int OP_BYTES = 128 * TC_RB * 2;          // 32 KB canonical operand
     static constexpr int G_LD = LP + 1;
     static constexpr int G_BYTES = LP * G_LD * 8;
